@@ -1,0 +1,146 @@
+// qboot_b200 -- exp / pow on the fixed-limb float (host + device).
+//
+// The reference calls mpfr_pow / mpfr_ui_pow on the table path (src/hor_recursion.cpp:43 `pow(4, Delta)`,
+// include/qboot/algebra/real_function.hpp:262 `pow(x, pow_)`), which are correctly rounded.  Here x^y is evaluated as
+// exp(y * ln x) in an extended format of E = L + QB_EXT_LIMBS limbs (ln x and ln 2 are supplied at that width) and
+// rounded once to `prec` bits.  The extended result carries a relative error below 2^-(32L + 50), so the final
+// rounding equals the correct rounding unless the exact value lies within that distance of a rounding boundary.
+#pragma once
+
+#include "mpf.cuh"
+
+#ifndef QB_EXT_LIMBS
+#define QB_EXT_LIMBS 3
+#endif
+
+namespace qb
+{
+	// widen / narrow ---------------------------------------------------------------------------------------------------
+	template <int E, int L>
+	QB_HD QB_INLINE void widen(mpf<E>& r, const mpf<L>& a)
+	{
+		static_assert(E >= L, "widen");
+		r.sk = a.sk;
+		r.exp = a.exp;
+		for (int i = 0; i < E - L; ++i) r.m[i] = 0u;
+		for (int i = 0; i < L; ++i) r.m[E - L + i] = a.m[i];
+	}
+	template <int L, int E>
+	QB_HD QB_INLINE void narrow(mpf<L>& r, const mpf<E>& a, int prec)
+	{
+		if (kind(a) != K_REG)
+		{
+			set_zero(r, a.sk);
+			r.sk = a.sk;
+			return;
+		}
+		round_to<L, E>(r, a.sk, a.exp, a.m, 0u, prec);
+	}
+	// top 53 bits as a double (truncated); zero/regular only
+	template <int E>
+	QB_HD double to_double(const mpf<E>& a)
+	{
+		if (kind(a) != K_REG) return 0.0;
+		uint64_t hi = (uint64_t(a.m[E - 1]) << 32) | (E >= 2 ? a.m[E - 2] : 0u);
+		double d = double(hi >> 11) * (1.0 / 9007199254740992.0);  // [0.5, 1)
+		// scale by 2^exp without libm dependencies on device
+		int32_t e = a.exp;
+		if (e > 1000) e = 1000;
+		if (e < -1000) e = -1000;
+		double s = 1.0;
+		double base = e >= 0 ? 2.0 : 0.5;
+		uint32_t n = uint32_t(e >= 0 ? e : -e);
+		while (n)
+		{
+			if (n & 1u) s *= base;
+			base *= base;
+			n >>= 1;
+		}
+		d *= s;
+		return sign(a) ? -d : d;
+	}
+
+	// r = exp(t), all in E limbs at 32E bits.  ln2 = ln 2 at the same width.
+	template <int E>
+	QB_HD void exp_ext(mpf<E>& r, const mpf<E>& t, const mpf<E>& ln2)
+	{
+		const int pe = 32 * E;
+		if (is_zero(t))
+		{
+			set_si(r, 1, pe);
+			return;
+		}
+		// k = nearest integer to t / ln 2
+		double td = to_double(t);
+		double kd = td * 1.4426950408889634;
+		int64_t k = int64_t(kd + (kd >= 0 ? 0.5 : -0.5));
+		mpf<E> x, u;
+		mul_si(u, ln2, k, pe);
+		sub(x, t, u, pe);  // |x| <~ 0.35 (+ slack)
+		const int s = 24;
+		if (kind(x) == K_REG) x.exp -= s;
+		// Taylor: sum = 1 + x + x^2/2! + ...
+		mpf<E> sum, term;
+		set_si(sum, 1, pe);
+		copy(term, x);
+		for (int n = 1; n < 4 * E + 16; ++n)
+		{
+			if (is_zero(term)) break;
+			if (term.exp < -pe - 4) break;
+			add(sum, sum, term, pe);
+			mul(u, term, x, pe);
+			div_si(term, u, n + 1, pe);
+		}
+		for (int i = 0; i < s; ++i)
+		{
+			mul(u, sum, sum, pe);
+			copy(sum, u);
+		}
+		copy(r, sum);
+		r.exp += int32_t(k);
+	}
+
+	// r = RN_prec(exp(y * lnx)),  lnx and ln2 given in E = L + QB_EXT_LIMBS limbs
+	template <int L>
+	QB_HD void pow_from_log(mpf<L>& r, const mpf<L + QB_EXT_LIMBS>& lnx, const mpf<L>& y,
+	                        const mpf<L + QB_EXT_LIMBS>& ln2, int prec)
+	{
+		constexpr int E = L + QB_EXT_LIMBS;
+		mpf<E> ye, t, v;
+		widen(ye, y);
+		mul(t, ye, lnx, 32 * E);
+		exp_ext(v, t, ln2);
+		narrow(r, v, prec);
+	}
+
+#if !defined(__CUDACC__)
+	// test harness hook (tests/hostemu): consts = [ln2 (E+2 words), lnx (E+2 words)]
+	template <int L>
+	bool hostemu_math(int prec, int op, const mpf<L>& x, const mpf<L>& y, int64_t p, const uint32_t* consts, mpf<L>& r)
+	{
+		constexpr int E = L + QB_EXT_LIMBS;
+		if (!consts) return false;
+		const mpf<E>* c = reinterpret_cast<const mpf<E>*>(consts);
+		(void)p;
+		if (op == 13)
+		{
+			pow_from_log<L>(r, c[1], y, c[0], prec);  // x^y with ln x = c[1]
+			return true;
+		}
+		if (op == 14)
+		{
+			pow_from_log<L>(r, c[1], x, c[0], prec);  // p^x with ln p = c[1]
+			return true;
+		}
+		if (op == 15)
+		{
+			mpf<E> xe, v;
+			widen(xe, x);
+			exp_ext(v, xe, c[0]);
+			narrow(r, v, prec);
+			return true;
+		}
+		return false;
+	}
+#endif
+}  // namespace qb

@@ -1,0 +1,78 @@
+// TEST HARNESS ONLY: compiles the engine's `__host__ __device__` multiprecision routines (qboot_b200/csrc/mpf.cuh)
+// for the host so that the CPU test-suite (-m "not gpu") can pin them bit-for-bit against MPFR (oracle/_ref).
+// Nothing in the product links or loads this file.
+#include <cstdint>
+#include <cstring>
+
+#include "../../qboot_b200/csrc/mpf.cuh"
+#include "../../qboot_b200/csrc/mpf_math.cuh"
+
+namespace
+{
+	template <int L>
+	int run(int prec, int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c, const int64_t* ia,
+	        const int64_t* ib, uint32_t* out, const uint32_t* consts)
+	{
+		using T = qb::mpf<L>;
+		static_assert(sizeof(T) == 4 * (L + 2), "layout");
+		const T* A = reinterpret_cast<const T*>(a);
+		const T* B = reinterpret_cast<const T*>(b);
+		const T* Cc = reinterpret_cast<const T*>(c);
+		T* O = reinterpret_cast<T*>(out);
+		T zero;
+		qb::set_zero(zero);
+		for (int i = 0; i < n; ++i)
+		{
+			const T& x = a ? A[i] : zero;
+			const T& y = b ? B[i] : zero;
+			const T& z = c ? Cc[i] : zero;
+			int64_t p = ia ? ia[i] : 0, q = ib ? ib[i] : 1;
+			T r;
+			qb::set_zero(r);
+			switch (op)
+			{
+			case 0: qb::add(r, x, y, prec); break;
+			case 1: qb::sub(r, x, y, prec); break;
+			case 2: qb::mul(r, x, y, prec); break;
+			case 3: qb::div(r, x, y, prec); break;
+			case 4: qb::fma(r, x, y, z, prec); break;
+			case 6: qb::mul_si(r, x, p, prec); break;
+			case 7: qb::add_si(r, x, p, prec); break;
+			case 8: qb::div_si(r, x, p, prec); break;
+			case 9: qb::mul_q(r, x, p, uint32_t(q), prec); break;
+			case 10: qb::div_q(r, x, p, uint32_t(q), prec); break;
+			case 11: qb::add_q(r, x, p, uint32_t(q), prec); break;
+			case 12: qb::set_q(r, p, uint32_t(q), prec); break;
+			case 18: qb::si_sub(r, p, x, prec); break;
+			case 20: qb::sub_q(r, x, p, uint32_t(q), prec); break;
+			case 22: qb::set_ui_2exp(r, uint64_t(p), int32_t(q), prec); break;
+			case 23: r.sk = uint32_t(qb::cmp(x, y) + 1); break;
+			case 24: r.sk = qb::is_integer(x) ? 1u : 0u; break;
+			case 13:  // pow(x, y) with x > 0 given ln(x) in consts (extended precision)
+			case 14:  // ui_pow
+			case 15:  // exp
+				if (!qb::hostemu_math<L>(prec, op, x, y, p, consts, r)) return -2;
+				break;
+			default: return -1;
+			}
+			O[i] = r;
+		}
+		return 0;
+	}
+}  // namespace
+
+#define QB_FOR_L(X) X(2) X(3) X(4) X(5) X(8) X(16) X(19) X(25) X(32) X(38) X(48)
+
+extern "C" int qbh_op(int prec, int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c,
+                      const int64_t* ia, const int64_t* ib, uint32_t* out, const uint32_t* consts)
+{
+	int L = (prec + 31) / 32;
+	switch (L)
+	{
+#define X(LL) \
+	case LL: return run<LL>(prec, op, n, a, b, c, ia, ib, out, consts);
+		QB_FOR_L(X)
+#undef X
+	default: return -100;
+	}
+}
