@@ -1,0 +1,230 @@
+// qboot_b200 -- from the rho-series to the block-derivative table and the F/H blocks (host + device building blocks).
+//
+//   deriv_*          : (1/k!) d^k/drho^k [ (4 rho)^Delta h(rho) ] at rho*, k = 0..lambda
+//                      (reference: gBlock_real, src/hor_recursion.cpp:40-56; RealFunctionWithPower::derivate /
+//                      approximate, include/qboot/algebra/real_function.hpp:236-264)
+//   rho_to_z         : rho-Taylor -> z-Taylor coefficients (RealConverter::convert, real_function.hpp:208-213,
+//                      dot(Vector, Matrix), include/qboot/algebra/matrix.hpp:444-456)
+//   expand_off_diag  : transverse derivatives by the Casimir recursion (Context::expand_off_diagonal, src/context.cpp:62-133)
+//   v_to_d           : table of ((1-z)(1-zbar))^d (src/context.cpp:28-42)
+//   fblock_entry     : one entry of 2 * proj_sym(v^d * g) (Context::F_block, include/qboot/context.hpp:123-128;
+//                      ComplexFunction mul / proj, include/qboot/algebra/complex_function.hpp:190-206)
+//
+// Every function performs the reference's operations in the reference's order, each rounded at `prec` bits.
+#pragma once
+
+#include "hor.cuh"
+#include "mpf_math.cuh"
+
+namespace qb
+{
+	// packed index of (dx, dy) in a Mixed table of order lambda: dy-major, dx-minor (complex_function.hpp:72-81)
+	QB_HD QB_INLINE int cf_index(int lambda, int dx, int dy) { return (lambda + 2 - dy) * dy + dx; }
+	QB_HD QB_INLINE int cf_dim(int lambda) { return (lambda + 2) * (lambda + 2) / 4; }
+	// packed index inside one parity class (sym 0 = Even, 1 = Odd)
+	QB_HD QB_INLINE int cf_index_sym(int lambda, int sym, int dx, int dy)
+	{
+		return sym == 0 ? (lambda / 2 * 2 + 3 - dy) * dy / 2 + dx / 2 : ((lambda - 1) / 2 * 2 + 3 - dy) * dy / 2 + (dx - 1) / 2;
+	}
+	QB_HD QB_INLINE int cf_dim_sym(int lambda, int sym)
+	{
+		int h = sym == 0 ? (lambda + 2) / 2 : (lambda + 1) / 2;
+		return h * (h + 1) / 2;
+	}
+
+	// ---- rho-derivatives ---------------------------------------------------------------------------------------------
+	// level-k scaling of one coefficient: a <- a * (q + n)          (derivate, real_function.hpp:236-240)
+	template <int L>
+	QB_HD QB_INLINE void deriv_scale(mpf<L>& a, const mpf<L>& a_prev, const mpf<L>& q, uint32_t n, int prec)
+	{
+		mpf<L> f;
+		add_si(f, q, int64_t(n), prec);
+		mul(a, a_prev, f, prec);
+	}
+	// Horner step s <- s * rho + a                                   (approximate, real_function.hpp:248-259)
+	template <int L>
+	QB_HD QB_INLINE void deriv_horner(mpf<L>& s, const mpf<L>& rho, const mpf<L>& a, int prec)
+	{
+		fma(s, s, rho, a, prec);
+	}
+	// f_k = s * rho^q / k!                                           (real_function.hpp:262, hor_recursion.cpp:46-53)
+	template <int L>
+	QB_HD void deriv_finish(mpf<L>& f, const mpf<L>& s, const mpf<L>& rho_pow_q, const mpf<L>& kfact, uint32_t k, int prec)
+	{
+		mul(f, s, rho_pow_q, prec);
+		if (k >= 1) div(f, f, kfact, prec);
+	}
+
+	// z[i] = x[0] * M[0][i], then += x[j] * M[j][i]                  (dot, matrix.hpp:444-456); M row-major (lambda+1)^2
+	template <int L>
+	QB_HD void rho_to_z_entry(mpf<L>& z, const mpf<L>* x, int64_t xstride, const mpf<L>* M, int lambda, int i, int prec)
+	{
+		mpf<L> t;
+		mul(z, x[0], M[i], prec);
+		for (int j = 1; j <= lambda; ++j)
+		{
+			mul(t, x[int64_t(j) * xstride], M[j * (lambda + 1) + i], prec);
+			add(z, z, t, prec);
+		}
+	}
+
+	// ---- transverse recursion ------------------------------------------------------------------------------------------
+	// quad_casimir4 = 4 * ((2 eps + spin) spin / 2 + (Delta / 2 - eps - 1) Delta)    (primary_op.hpp:60-63, context.cpp:70)
+	template <int L>
+	QB_HD void quad_casimir4(mpf<L>& r, const mpf<L>& D, uint32_t spin, Rational eps, int prec)
+	{
+		mpf<L> t;
+		div_si(t, D, 2, prec);
+		sub_q(t, t, eps.num, eps.den, prec);
+		add_si(t, t, -1, prec);
+		mul(t, t, D, prec);
+		// rational part (2 eps + spin) * spin / 2 = (2 num + spin den) spin / (2 den)
+		int64_t rn = (2 * eps.num + int64_t(spin) * int64_t(eps.den)) * int64_t(spin);
+		uint32_t rd = 2u * eps.den;
+		add_q(t, t, rn, rd, prec);
+		mul_si(r, t, 4, prec);
+	}
+
+	// One row entry of the recursion: everything except the same-row correction, i.e. val / common_factor.
+	// f is the Mixed table (packed), rows n-1 and n-2 must be complete.                         (context.cpp:72-121)
+	template <int L>
+	QB_HD void offdiag_val(mpf<L>& val, const mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& S,
+	                       const mpf<L>& P, const mpf<L>& qc4, Rational eps, int prec)
+	{
+		mpf<L> term, t2;
+#define QB_F(mm, nn) f[int64_t(cf_index(lambda, (mm), (nn))) * fs]
+		// h[m + 2, n - 1]
+		mul_si(val, QB_F(m + 2, n - 1), -int64_t(m + 1) * (m + 2), prec);
+		// h[m + 1, n - 1]
+		add_q(term, S, eps.num, eps.den, prec);
+		mul_si(term, term, 2, prec);
+		add_si(term, term, -int64_t(m + 4 * n - 6), prec);
+		mul_si(term, term, 2 * (m + 1), prec);
+		mul(term, term, QB_F(m + 1, n - 1), prec);
+		add(val, val, term, prec);
+		// h[m, n - 1]
+		set_q(term, eps.num * int64_t(4 * (m + n - 1)), eps.den, prec);
+		add_si(term, term, int64_t(m) * (m + 8 * n - 5) + int64_t(n) * (4 * n - 2) - 2, prec);
+		mul_si(t2, P, 2, prec);
+		add(term, term, t2, prec);
+		mul_si(t2, S, int64_t(8 * n + 4 * m - 8), prec);
+		add(term, term, t2, prec);
+		add(term, term, qc4, prec);
+		mul_si(term, term, 4, prec);
+		mul(term, term, QB_F(m, n - 1), prec);
+		add(val, val, term, prec);
+		// h[m - 1, n - 1]
+		if (m >= 1)
+		{
+			set_q(term, eps.num * int64_t(2 * (m + 1 - 2 * n)), eps.den, prec);
+			add_si(term, term, int64_t(m) * (m + 12 * n - 13) + int64_t(n) * (12 * n - 34) + 22, prec);
+			mul_si(t2, P, 2, prec);
+			add(term, term, t2, prec);
+			mul_si(t2, S, int64_t(8 * n + 2 * m - 10), prec);
+			add(term, term, t2, prec);
+			mul_si(term, term, 8, prec);
+			mul(term, term, QB_F(m - 1, n - 1), prec);
+			add(val, val, term, prec);
+		}
+		// h[m + 1, n - 2] and h[m + 2, n - 2]
+		if (n >= 2)
+		{
+			set_q(term, -2 * eps.num, eps.den, prec);
+			add_si(term, term, int64_t(3 * m + 4 * n - 6), prec);
+			mul_si(t2, S, 2, prec);
+			add(term, term, t2, prec);
+			mul_si(term, term, int64_t(8 * (m + 1)), prec);
+			mul(term, term, QB_F(m + 1, n - 2), prec);
+			mul_si(t2, QB_F(m + 2, n - 2), int64_t(4 * (m + 1) * (m + 2)), prec);
+			add(term, term, t2, prec);
+			add(val, val, term, prec);
+		}
+#undef QB_F
+		// common_factor = 4 n eps + (4 n - 2) n
+		int64_t cn = int64_t(4 * n) * eps.num + int64_t(4 * n - 2) * int64_t(n) * int64_t(eps.den);
+		div_q(val, val, cn, eps.den, prec);
+	}
+	// h[m, n] = val + 8 h[m-3, n] + 4 h[m-2, n] - 2 h[m-1, n]                                  (context.cpp:123-130)
+	template <int L>
+	QB_HD void offdiag_close(mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& val, int prec)
+	{
+		mpf<L> term, t2;
+		set_zero(term);
+		if (m >= 3)
+		{
+			mul_si(t2, f[int64_t(cf_index(lambda, m - 3, n)) * fs], 8, prec);
+			add(term, term, t2, prec);
+		}
+		if (m >= 2)
+		{
+			mul_si(t2, f[int64_t(cf_index(lambda, m - 2, n)) * fs], 4, prec);
+			add(term, term, t2, prec);
+		}
+		if (m >= 1)
+		{
+			mul_si(t2, f[int64_t(cf_index(lambda, m - 1, n)) * fs], 2, prec);
+			sub(term, term, t2, prec);
+		}
+		add(f[int64_t(cf_index(lambda, m, n)) * fs], val, term, prec);
+	}
+	// whole table, serial: f row 0 (dx = 0..lambda) must be filled
+	template <int L>
+	QB_HD void expand_off_diag(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& D, uint32_t spin, const mpf<L>& S,
+	                           const mpf<L>& P, Rational eps, int prec)
+	{
+		mpf<L> qc4, val;
+		quad_casimir4(qc4, D, spin, eps, prec);
+		for (int n = 1; n <= lambda / 2; ++n)
+			for (int m = 0; m + 2 * n <= lambda; ++m)
+			{
+				offdiag_val(val, f, fs, lambda, m, n, S, P, qc4, eps, prec);
+				offdiag_close(f, fs, lambda, m, n, val, prec);
+			}
+	}
+
+	// ---- v^d table -------------------------------------------------------------------------------------------------------
+	// f(0,0) = 4^-d given (pow); f(0,n) = f(0,n-1) * 4 * (-d + (n-1)) / n; f(m,n) = f(m-1,n) * (-4 d + 2 (m+2n-1)) / m
+	template <int L>
+	QB_HD void v_to_d_table(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& d, const mpf<L>& four_pow_minus_d, int prec)
+	{
+		mpf<L> md, t, u;
+		copy(md, d);
+		neg(md);
+		copy(f[0], four_pow_minus_d);
+		for (int n = 0; n <= lambda / 2; ++n)
+		{
+			if (n > 0)
+			{
+				mul_si(t, f[int64_t(cf_index(lambda, 0, n - 1)) * fs], 4, prec);
+				add_si(u, md, int64_t(n - 1), prec);
+				mul(t, t, u, prec);
+				div_si(f[int64_t(cf_index(lambda, 0, n)) * fs], t, int64_t(n), prec);
+			}
+			for (int m = 1; m + 2 * n <= lambda; ++m)
+			{
+				mul_si(u, d, -4, prec);
+				add_si(u, u, int64_t(2 * (m + 2 * n - 1)), prec);
+				mul(t, f[int64_t(cf_index(lambda, m - 1, n)) * fs], u, prec);
+				div_si(f[int64_t(cf_index(lambda, m, n)) * fs], t, int64_t(m), prec);
+			}
+		}
+	}
+
+	// ---- F / H block -------------------------------------------------------------------------------------------------------
+	// out = 2 * sum_{dy1 <= N} sum_{dx1 <= M} v(dx1, dy1) * g(M - dx1, N - dy1), accumulated in that order
+	template <int L>
+	QB_HD void fblock_entry(mpf<L>& out, const mpf<L>* v, int64_t vs, const mpf<L>* g, int64_t gs, int lambda, int M, int N,
+	                        int prec)
+	{
+		mpf<L> acc, t;
+		set_zero(acc);
+		for (int dy1 = 0; dy1 <= N; ++dy1)
+			for (int dx1 = 0; dx1 <= M; ++dx1)
+			{
+				// (dx1, dy1) must itself be a valid index: dx1 + 2 dy1 <= lambda holds since dx1 <= M, dy1 <= N, M + 2N <= lambda
+				mul(t, v[int64_t(cf_index(lambda, dx1, dy1)) * vs], g[int64_t(cf_index(lambda, M - dx1, N - dy1)) * gs], prec);
+				add(acc, acc, t, prec);
+			}
+		mul_si(out, acc, 2, prec);
+	}
+}  // namespace qb

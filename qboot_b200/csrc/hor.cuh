@@ -1,0 +1,218 @@
+// qboot_b200 -- Hogervorst-Osborn-Rychkov series recurrence on the fixed-limb float (host + device).
+//
+//   rec_coeffs   : coefficients of  sum_i p_i(n) b[n-i] = 0   (reference: _get_rec_coeffs, include/qboot/hor_formula.hpp:34-39,
+//                  src/hor_formula.cpp:8-296 spin 0, :298-2055 spin > 0)
+//   series_step  : b[n] = -(sum_{i=1}^{min(n,K-1)} p_i(n) b[n-i]) / p_0(n)   (src/hor_recursion.cpp:31-37)
+//
+// The middle polynomials p_1..p_{K-2} come from the integer tensors in hor_table.inc (tools/derive_hor_table.py);
+// each coefficient is evaluated monomial by monomial in lexicographic order, every product and every partial sum
+// rounded at `prec` bits, which reproduces the reference's MPFR evaluation bit for bit.
+#pragma once
+
+#include "mpf.cuh"
+
+namespace qb
+{
+	struct HorMono
+	{
+		int32_t c;
+		uint8_t eD, eS, eP, el, ee;
+	};
+	struct HorPoly
+	{
+		int32_t first, count, konst, flag;
+	};
+	// epsilon = (dim - 2) / 2 as an exact rational
+	struct Rational
+	{
+		int64_t num;
+		uint32_t den;
+	};
+
+	// value of one monomial |c| * Delta^a S^b P^c spin^d eps^e (sign handled by the caller unless `signed_c`)
+	template <int L>
+	QB_HD void hor_monomial(mpf<L>& t, const HorMono& mo, bool signed_c, const mpf<L>& D, const mpf<L>& S,
+	                        const mpf<L>& P, uint32_t spin, Rational eps, int prec)
+	{
+		int64_t c = mo.c;
+		if (!signed_c && c < 0) c = -c;
+		int nD = mo.eD, nS = mo.eS, nP = mo.eP, nl = mo.el, ne = mo.ee;
+		// leading factor
+		if (nD)
+		{
+			if (c == 1)
+				copy(t, D);
+			else
+				mul_si(t, D, c, prec);
+			--nD;
+		}
+		else if (nS)
+		{
+			if (c == 1)
+				copy(t, S);
+			else
+				mul_si(t, S, c, prec);
+			--nS;
+		}
+		else if (nP)
+		{
+			if (c == 1)
+				copy(t, P);
+			else
+				mul_si(t, P, c, prec);
+			--nP;
+		}
+		else if (nl)
+		{
+			// integer arithmetic: exact
+			int64_t v = c;
+			for (; nl > 0; --nl) v *= int64_t(spin);
+			set_si(t, v, prec);
+		}
+		else
+		{
+			set_q(t, c * eps.num, eps.den, prec);
+			--ne;
+		}
+		for (; nD > 0; --nD) mul(t, t, D, prec);
+		for (; nS > 0; --nS) mul(t, t, S, prec);
+		for (; nP > 0; --nP) mul(t, t, P, prec);
+		for (; nl > 0; --nl) mul_si(t, t, int64_t(spin), prec);
+		for (; ne > 0; --ne) mul_q(t, t, eps.num, eps.den, prec);
+	}
+
+	// one coefficient a[i][d]
+	template <int L>
+	QB_HD void hor_coefficient(mpf<L>& r, const HorPoly& po, const HorMono* monos, const mpf<L>& D, const mpf<L>& S,
+	                           const mpf<L>& P, uint32_t spin, Rational eps, int prec)
+	{
+		mpf<L> acc, t;
+		if (po.count == 0)
+			set_si(acc, po.konst, prec);
+		else
+		{
+			hor_monomial(acc, monos[po.first], true, D, S, P, spin, eps, prec);
+			for (int k = 1; k < po.count; ++k)
+			{
+				const HorMono& mo = monos[po.first + k];
+				hor_monomial(t, mo, false, D, S, P, spin, eps, prec);
+				add(acc, acc, t, prec, mo.c < 0);
+			}
+			add_si(acc, acc, po.konst, prec);
+		}
+		if (po.flag == 1)
+		{
+			// times (3 - 2 Delta + 2 eps)
+			mpf<L> lin, e2;
+			mul_si(lin, D, -2, prec);
+			set_q(e2, 2 * eps.num, eps.den, prec);
+			add(lin, lin, e2, prec);
+			add_si(lin, lin, 3, prec);
+			mul(r, lin, acc, prec);
+		}
+		else
+			copy(r, acc);
+	}
+
+	// c[0..m] (degree m) times (n + a)  ->  c[0..m+1]     (reference: Polynomial::_mul_linear, src/algebra/polynomial.cpp:76-83)
+	template <int L>
+	QB_HD void mul_linear(mpf<L>* c, int m, const mpf<L>& a, int prec)
+	{
+		// in place, top down: new[m+1] = c[m]; new[i] = c[i] * a + c[i-1]; new[0] = c[0] * a
+		copy(c[m + 1], c[m]);
+		for (int i = m; i >= 1; --i) fma(c[i], c[i], a, c[i - 1], prec);
+		mul(c[0], c[0], a, prec);
+	}
+
+	// All recurrence coefficients of one table: out[i * (deg + 1) + d], i < K, K = 6 / deg = 3 for spin 0, else 8 / 4.
+	template <int L>
+	QB_HD void rec_coeffs(mpf<L>* out, const mpf<L>& D, uint32_t spin, const mpf<L>& S, const mpf<L>& P, Rational eps,
+	                      int prec, const HorPoly* polys, const HorMono* monos)
+	{
+		const int K = spin == 0 ? 6 : 8, deg = spin == 0 ? 3 : 4, st = deg + 1;
+		for (int i = 1; i < K - 1; ++i)
+			for (int d = 0; d <= deg; ++d)
+				hor_coefficient(out[i * st + d], polys[(i - 1) * st + d], monos, D, S, P, spin, eps, prec);
+		mpf<L> a;
+		mpf<L>* p0 = out;
+		mpf<L>* pl = out + (K - 1) * st;
+		if (spin == 0)
+		{
+			// p_0 = n (n + Delta - 1) (n + 2 Delta - 2 eps - 2)
+			set_zero(p0[0]);
+			set_si(p0[1], 1, prec);
+			add_si(a, D, -1, prec);
+			mul_linear(p0, 1, a, prec);
+			mul_si(a, D, 2, prec);
+			sub_q(a, a, 2 * eps.num + 2 * int64_t(eps.den), eps.den, prec);
+			mul_linear(p0, 2, a, prec);
+			// p_5 = (n + Delta - 4) (n + 2 Delta - 5) (n + 2 eps - 3)
+			add_si(pl[0], D, -4, prec);
+			set_si(pl[1], 1, prec);
+			mul_si(a, D, 2, prec);
+			add_si(a, a, -5, prec);
+			mul_linear(pl, 1, a, prec);
+			set_q(a, 2 * eps.num - 3 * int64_t(eps.den), eps.den, prec);
+			mul_linear(pl, 2, a, prec);
+		}
+		else
+		{
+			// p_0 = -n (n + Delta + spin - 1) (n + 2 Delta - 2 eps - 2) (n + Delta - 2 eps - spin - 1)
+			set_zero(p0[0]);
+			set_si(p0[1], -1, prec);
+			add_si(a, D, int64_t(spin) - 1, prec);
+			mul_linear(p0, 1, a, prec);
+			mul_si(a, D, 2, prec);
+			sub_q(a, a, 2 * eps.num, eps.den, prec);
+			add_si(a, a, -2, prec);
+			mul_linear(p0, 2, a, prec);
+			sub_q(a, D, 2 * eps.num, eps.den, prec);
+			add_si(a, a, -int64_t(spin), prec);
+			add_si(a, a, -1, prec);
+			mul_linear(p0, 3, a, prec);
+			// p_7 = (n + 2 Delta - 7) (n + 2 eps - 5) (n + Delta - spin - 6) (n + Delta + 2 eps + spin - 6)
+			mul_si(pl[0], D, 2, prec);
+			add_si(pl[0], pl[0], -7, prec);
+			set_si(pl[1], 1, prec);
+			set_q(a, 2 * eps.num - 5 * int64_t(eps.den), eps.den, prec);
+			mul_linear(pl, 1, a, prec);
+			add_si(a, D, -(int64_t(spin) + 6), prec);
+			mul_linear(pl, 2, a, prec);
+			add_q(a, D, 2 * eps.num + (int64_t(spin) - 6) * int64_t(eps.den), eps.den, prec);
+			mul_linear(pl, 3, a, prec);
+		}
+	}
+
+	// p(n) by Horner with the integer n: s = s * n, s = s + c   (include/qboot/algebra/polynomial.hpp:66-83)
+	template <int L>
+	QB_HD void poly_eval_ui(mpf<L>& s, const mpf<L>* c, int deg, uint32_t n, int prec)
+	{
+		copy(s, c[deg]);
+		for (int d = deg - 1; d >= 0; --d)
+		{
+			mul_si(s, s, int64_t(n), prec);
+			add(s, s, c[d], prec);
+		}
+	}
+
+	// b[0] .. b[n_max] of one table, b[0] given.  `coef` from rec_coeffs.  b is addressed as b[n * stride].
+	template <int L>
+	QB_HD void series(mpf<L>* b, int64_t stride, uint32_t n_max, const mpf<L>* coef, uint32_t spin, int prec)
+	{
+		const int K = spin == 0 ? 6 : 8, deg = spin == 0 ? 3 : 4, st = deg + 1;
+		mpf<L> sum, pv;
+		for (uint32_t n = 1; n <= n_max; ++n)
+		{
+			set_zero(sum);
+			for (int i = 1; i < K; ++i)
+				if (uint32_t(i) <= n)
+				{
+					poly_eval_ui(pv, coef + i * st, deg, n, prec);
+					fma(sum, pv, b[int64_t(n - uint32_t(i)) * stride], sum, prec);
+				}
+			neg(sum);
+			poly_eval_ui(pv, coef, deg, n, prec);
+			div(b[int64_t(n) * stride], sum, pv, prec);
+		}
+	}
+}  // namespace qb
