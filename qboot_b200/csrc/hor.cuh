@@ -124,6 +124,68 @@ namespace qb
 		mul(c[0], c[0], a, prec);
 	}
 
+	// p_0 (first == true) or p_{K-1}: products of linear factors (n + a), built by repeated mul_linear exactly as the
+	// reference does (src/hor_formula.cpp:16-19,291-294 spin 0; :306-311,2049-2054 spin > 0).  p[0..deg].
+	template <int L>
+	QB_HD void rec_coeffs_end(mpf<L>* p, const mpf<L>& D, uint32_t spin, Rational eps, int prec, bool first)
+	{
+		mpf<L> a;
+		if (spin == 0)
+		{
+			if (first)
+			{
+				// p_0 = n (n + Delta - 1) (n + 2 Delta - 2 eps - 2)
+				set_zero(p[0]);
+				set_si(p[1], 1, prec);
+				add_si(a, D, -1, prec);
+				mul_linear(p, 1, a, prec);
+				mul_si(a, D, 2, prec);
+				sub_q(a, a, 2 * eps.num + 2 * int64_t(eps.den), eps.den, prec);
+				mul_linear(p, 2, a, prec);
+			}
+			else
+			{
+				// p_5 = (n + Delta - 4) (n + 2 Delta - 5) (n + 2 eps - 3)
+				add_si(p[0], D, -4, prec);
+				set_si(p[1], 1, prec);
+				mul_si(a, D, 2, prec);
+				add_si(a, a, -5, prec);
+				mul_linear(p, 1, a, prec);
+				set_q(a, 2 * eps.num - 3 * int64_t(eps.den), eps.den, prec);
+				mul_linear(p, 2, a, prec);
+			}
+		}
+		else if (first)
+		{
+			// p_0 = -n (n + Delta + spin - 1) (n + 2 Delta - 2 eps - 2) (n + Delta - 2 eps - spin - 1)
+			set_zero(p[0]);
+			set_si(p[1], -1, prec);
+			add_si(a, D, int64_t(spin) - 1, prec);
+			mul_linear(p, 1, a, prec);
+			mul_si(a, D, 2, prec);
+			sub_q(a, a, 2 * eps.num, eps.den, prec);
+			add_si(a, a, -2, prec);
+			mul_linear(p, 2, a, prec);
+			sub_q(a, D, 2 * eps.num, eps.den, prec);
+			add_si(a, a, -int64_t(spin), prec);
+			add_si(a, a, -1, prec);
+			mul_linear(p, 3, a, prec);
+		}
+		else
+		{
+			// p_7 = (n + 2 Delta - 7) (n + 2 eps - 5) (n + Delta - spin - 6) (n + Delta + 2 eps + spin - 6)
+			mul_si(p[0], D, 2, prec);
+			add_si(p[0], p[0], -7, prec);
+			set_si(p[1], 1, prec);
+			set_q(a, 2 * eps.num - 5 * int64_t(eps.den), eps.den, prec);
+			mul_linear(p, 1, a, prec);
+			add_si(a, D, -(int64_t(spin) + 6), prec);
+			mul_linear(p, 2, a, prec);
+			add_q(a, D, 2 * eps.num + (int64_t(spin) - 6) * int64_t(eps.den), eps.den, prec);
+			mul_linear(p, 3, a, prec);
+		}
+	}
+
 	// All recurrence coefficients of one table: out[i * (deg + 1) + d], i < K, K = 6 / deg = 3 for spin 0, else 8 / 4.
 	template <int L>
 	QB_HD void rec_coeffs(mpf<L>* out, const mpf<L>& D, uint32_t spin, const mpf<L>& S, const mpf<L>& P, Rational eps,
@@ -133,54 +195,8 @@ namespace qb
 		for (int i = 1; i < K - 1; ++i)
 			for (int d = 0; d <= deg; ++d)
 				hor_coefficient(out[i * st + d], polys[(i - 1) * st + d], monos, D, S, P, spin, eps, prec);
-		mpf<L> a;
-		mpf<L>* p0 = out;
-		mpf<L>* pl = out + (K - 1) * st;
-		if (spin == 0)
-		{
-			// p_0 = n (n + Delta - 1) (n + 2 Delta - 2 eps - 2)
-			set_zero(p0[0]);
-			set_si(p0[1], 1, prec);
-			add_si(a, D, -1, prec);
-			mul_linear(p0, 1, a, prec);
-			mul_si(a, D, 2, prec);
-			sub_q(a, a, 2 * eps.num + 2 * int64_t(eps.den), eps.den, prec);
-			mul_linear(p0, 2, a, prec);
-			// p_5 = (n + Delta - 4) (n + 2 Delta - 5) (n + 2 eps - 3)
-			add_si(pl[0], D, -4, prec);
-			set_si(pl[1], 1, prec);
-			mul_si(a, D, 2, prec);
-			add_si(a, a, -5, prec);
-			mul_linear(pl, 1, a, prec);
-			set_q(a, 2 * eps.num - 3 * int64_t(eps.den), eps.den, prec);
-			mul_linear(pl, 2, a, prec);
-		}
-		else
-		{
-			// p_0 = -n (n + Delta + spin - 1) (n + 2 Delta - 2 eps - 2) (n + Delta - 2 eps - spin - 1)
-			set_zero(p0[0]);
-			set_si(p0[1], -1, prec);
-			add_si(a, D, int64_t(spin) - 1, prec);
-			mul_linear(p0, 1, a, prec);
-			mul_si(a, D, 2, prec);
-			sub_q(a, a, 2 * eps.num, eps.den, prec);
-			add_si(a, a, -2, prec);
-			mul_linear(p0, 2, a, prec);
-			sub_q(a, D, 2 * eps.num, eps.den, prec);
-			add_si(a, a, -int64_t(spin), prec);
-			add_si(a, a, -1, prec);
-			mul_linear(p0, 3, a, prec);
-			// p_7 = (n + 2 Delta - 7) (n + 2 eps - 5) (n + Delta - spin - 6) (n + Delta + 2 eps + spin - 6)
-			mul_si(pl[0], D, 2, prec);
-			add_si(pl[0], pl[0], -7, prec);
-			set_si(pl[1], 1, prec);
-			set_q(a, 2 * eps.num - 5 * int64_t(eps.den), eps.den, prec);
-			mul_linear(pl, 1, a, prec);
-			add_si(a, D, -(int64_t(spin) + 6), prec);
-			mul_linear(pl, 2, a, prec);
-			add_q(a, D, 2 * eps.num + (int64_t(spin) - 6) * int64_t(eps.den), eps.den, prec);
-			mul_linear(pl, 3, a, prec);
-		}
+		rec_coeffs_end(out, D, spin, eps, prec, true);
+		rec_coeffs_end(out + (K - 1) * st, D, spin, eps, prec, false);
 	}
 
 	// p(n) by Horner with the integer n: s = s * n, s = s + c   (include/qboot/algebra/polynomial.hpp:66-83)

@@ -6,6 +6,7 @@
 
 #include "../../qboot_b200/csrc/block.cuh"
 #include "../../qboot_b200/csrc/hor_table.inc"
+#include "../../qboot_b200/csrc/hostmath.hpp"
 
 #define QB_FOR_L(X) X(2) X(3) X(4) X(5) X(8) X(16) X(19) X(25) X(32) X(38) X(48)
 
@@ -110,10 +111,53 @@ namespace
 				}
 		return cnt;
 	}
+	template <int L>
+	int consts_t(int prec, uint32_t lambda, uint32_t* rho, uint32_t* mat, uint32_t* kfact, uint32_t* ext3)
+	{
+		qb::ContextConsts<L> c;
+		qb::make_context_consts<L>(c, lambda, prec);
+		std::memcpy(rho, &c.rho, sizeof(c.rho));
+		std::memcpy(mat, c.mat.data(), sizeof(qb::mpf<L>) * c.mat.size());
+		std::memcpy(kfact, c.kfact.data(), sizeof(qb::mpf<L>) * c.kfact.size());
+		constexpr int E = L + QB_EXT_LIMBS;
+		std::memcpy(ext3, &c.ln2e, sizeof(qb::mpf<E>));
+		std::memcpy(ext3 + (E + 2), &c.ln4e, sizeof(qb::mpf<E>));
+		std::memcpy(ext3 + 2 * (E + 2), &c.lnrhoe, sizeof(qb::mpf<E>));
+		return 0;
+	}
+	template <int L>
+	int sqrt_t(int prec, int n, const uint32_t* a, uint32_t* out)
+	{
+		using T = qb::mpf<L>;
+		for (int i = 0; i < n; ++i) qb::sqrt(reinterpret_cast<T*>(out)[i], reinterpret_cast<const T*>(a)[i], prec);
+		return 0;
+	}
 }  // namespace
 
 extern "C"
 {
+	int qbh_context_consts(int prec, uint32_t lambda, uint32_t* rho, uint32_t* mat, uint32_t* kfact, uint32_t* ext3)
+	{
+		switch ((prec + 31) / 32)
+		{
+#define X(LL) \
+	case LL: return consts_t<LL>(prec, lambda, rho, mat, kfact, ext3);
+			QB_FOR_L(X)
+#undef X
+		default: return -100;
+		}
+	}
+	int qbh_sqrt(int prec, int n, const uint32_t* a, uint32_t* out)
+	{
+		switch ((prec + 31) / 32)
+		{
+#define X(LL) \
+	case LL: return sqrt_t<LL>(prec, n, a, out);
+			QB_FOR_L(X)
+#undef X
+		default: return -100;
+		}
+	}
 	int qbh_gblock(int prec, uint32_t n_max, uint32_t lambda, int64_t en, uint32_t ed, const uint32_t* d, uint32_t spin,
 	               const uint32_t* S, const uint32_t* P, const uint32_t* b0, const uint32_t* rho, const uint32_t* mat,
 	               const uint32_t* consts_ext, uint32_t* out, uint32_t* out_real)
