@@ -1,0 +1,103 @@
+/* qboot_b200 -- C ABI of the B200 block-table engine.
+ *
+ * This is the drop-in boundary for qboot's one data-parallel hot path: conformal-block derivative tables
+ * gBlock(Delta, spin, S, P) and the F/H blocks built from them.  In the reference the path sits behind the memoised
+ * callables of `qboot::Context` (include/qboot/context.hpp:29-56,70-76,123-139, constructed in src/context.cpp:47-61)
+ * and the free functions of include/qboot/hor_recursion.hpp:19-30; a maintainer binds these entry points from
+ * `Context::gBlock` / `Context::evaluate`.
+ *
+ * Conventions
+ *   - plain C: ints, pointers and sizes only; every call returns 0 or a negative qb_status; nothing throws.
+ *   - one handle per GPU; calls on one handle must be serialised by the caller.
+ *   - buffers are owned by the caller; the library never frees caller memory.
+ *   - a number is a record of W = L + 2 uint32 words, L = ceil(prec / 32):
+ *       w[0]  kind | sign << 31   (kind 0 zero, 1 regular, 2 inf, 3 nan)
+ *       w[1]  exponent e (int32): value = 0.m * 2^e, the MPFR convention
+ *       w[2 .. 2+L)  mantissa limbs, least significant first, left aligned (top bit of w[L+1] set), rounded to prec
+ *     i.e. the content of the reference's `mp::real` (include/qboot/mp/real.hpp:87-112) at mp::global_prec = prec.
+ *   - all arithmetic is the reference's: each operation rounded once to nearest-even at `prec` bits, performed in the
+ *     reference's order, so outputs equal the reference's MPFR results bit for bit.
+ *   - there is no CPU fallback: without a CUDA device qb_create fails with QB_ERR_NO_DEVICE.
+ */
+#ifndef QBOOT_B200_H_
+#define QBOOT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qb_handle qb_handle;
+
+typedef enum
+{
+	QB_OK = 0,
+	QB_ERR_NO_DEVICE = -1,     /* no CUDA device / CUDA runtime error at creation */
+	QB_ERR_BAD_PREC = -2,      /* precision not among the compiled limb counts */
+	QB_ERR_NO_CONTEXT = -3,    /* qb_context_init has not been called */
+	QB_ERR_BAD_ARG = -4,
+	QB_ERR_CUDA = -5,          /* a CUDA call or kernel failed; see qb_last_cuda_error */
+	QB_ERR_RANGE = -6,         /* rational / spin out of the supported range */
+	QB_ERR_NO_MEMORY = -7
+} qb_status;
+
+/* Version string of the library. */
+const char* qb_version(void);
+const char* qb_strerror(int status);
+/* 1 if kernels for this precision were compiled in (limb count L = ceil(prec/32)), else 0. */
+int qb_precision_supported(int prec_bits);
+
+/* Handle = device + stream + scratch arena.  Replaces what `Context`'s two `_task_queue`s own in the reference
+ * (include/qboot/context.hpp:29-38).  prec_bits plays the role of mp::global_prec (src/mp/real.cpp:5). */
+int qb_create(int device, int prec_bits, qb_handle** out);
+void qb_destroy(qb_handle* h);
+int qb_words(const qb_handle* h);            /* W = L + 2 */
+const char* qb_last_cuda_error(const qb_handle* h);
+
+/* Context(n_Max, lambda, dim) -- src/context.cpp:47-61.  epsilon = (dim - 2) / 2 = eps_num / eps_den exactly.
+ * Computes rho = 3 - sqrt(8), the rho->z conversion matrix and the logarithm constants on the host and uploads them. */
+int qb_context_init(qb_handle* h, uint32_t n_max, uint32_t lambda, int64_t eps_num, uint32_t eps_den);
+/* Read back Context::rho() (W words) and the (lambda+1)^2 row-major rho->z matrix (Context::rho_to_z()). */
+int qb_context_get(const qb_handle* h, uint32_t* rho, uint32_t* rho_to_z);
+/* dim_M = (lambda+2)^2/4: numbers per table (function_dimension, include/qboot/algebra/complex_function.hpp:43-53) */
+int qb_table_dim(const qb_handle* h);
+/* numbers per F/H block: sym 0 = Even (H), 1 = Odd (F) */
+int qb_block_dim(const qb_handle* h, int sym);
+
+/* gBlock(op, S, P, context) for n operators -- src/hor_recursion.cpp:57-60 (a6 o a4 o a3 o a2 of SURVEY section 8).
+ *   spin[n]; delta, S, P: n records each (HOST memory); out: n * dim_M records (HOST memory) in the reference's
+ *   flatten() order (dy-major, dx-minor, complex_function.hpp:72-81).
+ * Unit operators (Delta = 0) and divergent operators (primary_op.hpp:68-77, averaged as in hor_recursion.cpp:21-28)
+ * are handled as the reference handles them. */
+int qb_gblock_batch(qb_handle* h, int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S,
+                    const uint32_t* P, uint32_t* out);
+
+/* The same in three steps, so that a caller (or a benchmark) can keep inputs and tables resident in HBM:
+ *   plan  : host-side planning (b[0], divergence test, job list) + upload of the inputs
+ *   run   : all kernels, asynchronous on the handle's stream
+ *   fetch : device -> host copy of the n * dim_M records                                                  */
+int qb_gblock_plan(qb_handle* h, int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S,
+                   const uint32_t* P);
+int qb_gblock_run(qb_handle* h);
+int qb_gblock_fetch(qb_handle* h, uint32_t* out);
+int qb_sync(qb_handle* h);
+/* device pointer of the resident tables of the last run (n * dim_M records), for callers that chain kernels */
+const uint32_t* qb_gblock_device_tables(const qb_handle* h);
+/* number of kernels launched by the library on this handle so far */
+int64_t qb_launch_count(const qb_handle* h);
+/* CUDA stream of the handle (cudaStream_t as an integer), for event timing on the launching stream */
+uint64_t qb_stream(const qb_handle* h);
+
+/* F/H blocks of m terms over the resident tables of the last qb_gblock_run -- Context::F_block / evaluate
+ * (include/qboot/context.hpp:123-139): out_term = 2 * proj_sym( v^d * g_table ).
+ *   table_idx[m] indexes the resident tables; d: n_d distinct records (HOST); d_idx[m] indexes d; sym[m] in {0, 1};
+ *   out: sum over terms of qb_block_dim(sym) records (HOST), terms in order. */
+int qb_fblock_batch(qb_handle* h, int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
+                    const int32_t* sym, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* QBOOT_B200_H_ */

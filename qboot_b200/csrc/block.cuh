@@ -49,7 +49,7 @@ namespace qb
 	}
 	// f_k = s * rho^q / k!                                           (real_function.hpp:262, hor_recursion.cpp:46-53)
 	template <int L>
-	QB_HD void deriv_finish(mpf<L>& f, const mpf<L>& s, const mpf<L>& rho_pow_q, const mpf<L>& kfact, uint32_t k, int prec)
+	QB_HD QB_NOINLINE void deriv_finish(mpf<L>& f, const mpf<L>& s, const mpf<L>& rho_pow_q, const mpf<L>& kfact, uint32_t k, int prec)
 	{
 		mul(f, s, rho_pow_q, prec);
 		if (k >= 1) div(f, f, kfact, prec);
@@ -57,7 +57,7 @@ namespace qb
 
 	// z[i] = x[0] * M[0][i], then += x[j] * M[j][i]                  (dot, matrix.hpp:444-456); M row-major (lambda+1)^2
 	template <int L>
-	QB_HD void rho_to_z_entry(mpf<L>& z, const mpf<L>* x, int64_t xstride, const mpf<L>* M, int lambda, int i, int prec)
+	QB_HD QB_NOINLINE void rho_to_z_entry(mpf<L>& z, const mpf<L>* x, int64_t xstride, const mpf<L>* M, int lambda, int i, int prec)
 	{
 		mpf<L> t;
 		mul(z, x[0], M[i], prec);
@@ -71,7 +71,7 @@ namespace qb
 	// ---- transverse recursion ------------------------------------------------------------------------------------------
 	// quad_casimir4 = 4 * ((2 eps + spin) spin / 2 + (Delta / 2 - eps - 1) Delta)    (primary_op.hpp:60-63, context.cpp:70)
 	template <int L>
-	QB_HD void quad_casimir4(mpf<L>& r, const mpf<L>& D, uint32_t spin, Rational eps, int prec)
+	QB_HD QB_NOINLINE void quad_casimir4(mpf<L>& r, const mpf<L>& D, uint32_t spin, Rational eps, int prec)
 	{
 		mpf<L> t;
 		div_si(t, D, 2, prec);
@@ -88,7 +88,7 @@ namespace qb
 	// One row entry of the recursion: everything except the same-row correction, i.e. val / common_factor.
 	// f is the Mixed table (packed), rows n-1 and n-2 must be complete.                         (context.cpp:72-121)
 	template <int L>
-	QB_HD void offdiag_val(mpf<L>& val, const mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& S,
+	QB_HD QB_NOINLINE void offdiag_val(mpf<L>& val, const mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& S,
 	                       const mpf<L>& P, const mpf<L>& qc4, Rational eps, int prec)
 	{
 		mpf<L> term, t2;
@@ -146,7 +146,7 @@ namespace qb
 	}
 	// h[m, n] = val + 8 h[m-3, n] + 4 h[m-2, n] - 2 h[m-1, n]                                  (context.cpp:123-130)
 	template <int L>
-	QB_HD void offdiag_close(mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& val, int prec)
+	QB_HD QB_NOINLINE void offdiag_close(mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& val, int prec)
 	{
 		mpf<L> term, t2;
 		set_zero(term);
@@ -169,7 +169,7 @@ namespace qb
 	}
 	// whole table, serial: f row 0 (dx = 0..lambda) must be filled
 	template <int L>
-	QB_HD void expand_off_diag(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& D, uint32_t spin, const mpf<L>& S,
+	QB_HD QB_NOINLINE void expand_off_diag(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& D, uint32_t spin, const mpf<L>& S,
 	                           const mpf<L>& P, Rational eps, int prec)
 	{
 		mpf<L> qc4, val;
@@ -185,7 +185,7 @@ namespace qb
 	// ---- v^d table -------------------------------------------------------------------------------------------------------
 	// f(0,0) = 4^-d given (pow); f(0,n) = f(0,n-1) * 4 * (-d + (n-1)) / n; f(m,n) = f(m-1,n) * (-4 d + 2 (m+2n-1)) / m
 	template <int L>
-	QB_HD void v_to_d_table(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& d, const mpf<L>& four_pow_minus_d, int prec)
+	QB_HD QB_NOINLINE void v_to_d_table(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& d, const mpf<L>& four_pow_minus_d, int prec)
 	{
 		mpf<L> md, t, u;
 		copy(md, d);
@@ -213,7 +213,7 @@ namespace qb
 	// ---- F / H block -------------------------------------------------------------------------------------------------------
 	// out = 2 * sum_{dy1 <= N} sum_{dx1 <= M} v(dx1, dy1) * g(M - dx1, N - dy1), accumulated in that order
 	template <int L>
-	QB_HD void fblock_entry(mpf<L>& out, const mpf<L>* v, int64_t vs, const mpf<L>* g, int64_t gs, int lambda, int M, int N,
+	QB_HD QB_NOINLINE void fblock_entry(mpf<L>& out, const mpf<L>* v, int64_t vs, const mpf<L>* g, int64_t gs, int lambda, int M, int N,
 	                        int prec)
 	{
 		mpf<L> acc, t;

@@ -1,0 +1,138 @@
+// qboot_b200 -- C ABI (include/qboot_b200.h) over the per-precision engines.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+
+#include "../../include/qboot_b200.h"
+#include "engine.cuh"
+
+#ifndef QB_L_LIST
+#error "QB_L_LIST must list the compiled limb counts, e.g. -DQB_L_LIST='X(19) X(25) X(32) X(48)'"
+#endif
+
+#define X(LL) extern "C" qb::EngineBase* qb_new_engine_L##LL(int device, int prec);
+QB_L_LIST
+#undef X
+
+struct qb_handle
+{
+	qb::EngineBase* e;
+};
+
+static qb::EngineFactory factory_for(int L)
+{
+	switch (L)
+	{
+#define X(LL) \
+	case LL: return &qb_new_engine_L##LL;
+		QB_L_LIST
+#undef X
+	default: return nullptr;
+	}
+}
+
+extern "C"
+{
+	const char* qb_version(void) { return "qboot_b200 0.1 (sm_100a)"; }
+	const char* qb_strerror(int s)
+	{
+		switch (s)
+		{
+		case QB_OK: return "ok";
+		case QB_ERR_NO_DEVICE: return "no usable CUDA device (this engine has no CPU fallback)";
+		case QB_ERR_BAD_PREC: return "no kernels compiled for this precision";
+		case QB_ERR_NO_CONTEXT: return "qb_context_init has not been called on this handle";
+		case QB_ERR_BAD_ARG: return "bad argument";
+		case QB_ERR_CUDA: return "CUDA error (see qb_last_cuda_error)";
+		case QB_ERR_RANGE: return "rational dimension or spin outside the supported range";
+		case QB_ERR_NO_MEMORY: return "device memory exhausted";
+		default: return "unknown status";
+		}
+	}
+	int qb_precision_supported(int prec) { return prec > 0 && factory_for((prec + 31) / 32) != nullptr; }
+
+	int qb_create(int device, int prec, qb_handle** out)
+	{
+		if (!out) return QB_ERR_BAD_ARG;
+		*out = nullptr;
+		if (prec < 64) return QB_ERR_BAD_PREC;
+		qb::EngineFactory f = factory_for((prec + 31) / 32);
+		if (!f) return QB_ERR_BAD_PREC;
+		int ndev = 0;
+		if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+		{
+			cudaGetLastError();
+			return QB_ERR_NO_DEVICE;
+		}
+		qb::EngineBase* e = f(device, prec);
+		if (!e) return QB_ERR_NO_DEVICE;
+		qb_handle* h = new (std::nothrow) qb_handle{e};
+		if (!h)
+		{
+			delete e;
+			return QB_ERR_NO_MEMORY;
+		}
+		*out = h;
+		return QB_OK;
+	}
+	void qb_destroy(qb_handle* h)
+	{
+		if (!h) return;
+		delete h->e;
+		delete h;
+	}
+	int qb_words(const qb_handle* h) { return h ? h->e->limbs + 2 : QB_ERR_BAD_ARG; }
+	const char* qb_last_cuda_error(const qb_handle* h) { return h ? h->e->cuda_error.c_str() : ""; }
+	int qb_context_init(qb_handle* h, uint32_t n_max, uint32_t lambda, int64_t en, uint32_t ed)
+	{
+		return h ? h->e->context_init(n_max, lambda, en, ed) : QB_ERR_BAD_ARG;
+	}
+	int qb_context_get(const qb_handle* h, uint32_t* rho, uint32_t* mat)
+	{
+		return h ? h->e->context_get(rho, mat) : QB_ERR_BAD_ARG;
+	}
+	int qb_table_dim(const qb_handle* h) { return h ? h->e->table_dim() : QB_ERR_BAD_ARG; }
+	int qb_block_dim(const qb_handle* h, int sym)
+	{
+		return (h && (sym == 0 || sym == 1)) ? h->e->block_dim(sym) : QB_ERR_BAD_ARG;
+	}
+	int qb_gblock_plan(qb_handle* h, int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S,
+	                   const uint32_t* P)
+	{
+		return h ? h->e->gblock_plan(n, spin, delta, S, P) : QB_ERR_BAD_ARG;
+	}
+	int qb_gblock_run(qb_handle* h) { return h ? h->e->gblock_run() : QB_ERR_BAD_ARG; }
+	int qb_gblock_fetch(qb_handle* h, uint32_t* out) { return (h && out) ? h->e->gblock_fetch(out) : QB_ERR_BAD_ARG; }
+	int qb_sync(qb_handle* h)
+	{
+		if (!h) return QB_ERR_BAD_ARG;
+		cudaSetDevice(h->e->device);
+		cudaError_t e = cudaStreamSynchronize(h->e->stream);
+		if (e != cudaSuccess)
+		{
+			h->e->cuda_error = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e);
+			return QB_ERR_CUDA;
+		}
+		return QB_OK;
+	}
+	const uint32_t* qb_gblock_device_tables(const qb_handle* h) { return h ? h->e->device_tables() : nullptr; }
+	int64_t qb_launch_count(const qb_handle* h) { return h ? h->e->launches : 0; }
+	uint64_t qb_stream(const qb_handle* h) { return h ? uint64_t(reinterpret_cast<uintptr_t>(h->e->stream)) : 0; }
+	int qb_gblock_batch(qb_handle* h, int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S,
+	                    const uint32_t* P, uint32_t* out)
+	{
+		if (!h) return QB_ERR_BAD_ARG;
+		int rc = h->e->gblock_plan(n, spin, delta, S, P);
+		if (rc) return rc;
+		rc = h->e->gblock_run();
+		if (rc) return rc;
+		if (n > 0 && !out) return QB_ERR_BAD_ARG;
+		return h->e->gblock_fetch(out);
+	}
+	int qb_fblock_batch(qb_handle* h, int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
+	                    const int32_t* sym, uint32_t* out)
+	{
+		return h ? h->e->fblock_batch(m, table_idx, n_d, d, d_idx, sym, out) : QB_ERR_BAD_ARG;
+	}
+}

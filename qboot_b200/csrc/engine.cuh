@@ -1,0 +1,421 @@
+// qboot_b200 -- per-precision engine behind the C ABI (include/qboot_b200.h): device buffers, host-side planning and
+// kernel launches.  One instantiation per limb count L lives in its own translation unit (engine_inst.cu, -DQB_L=..).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace qb
+{
+	// precision-erased interface used by capi.cu
+	struct EngineBase
+	{
+		int device = 0, prec = 0, limbs = 0;
+		cudaStream_t stream = nullptr;
+		std::string cuda_error;
+		int64_t launches = 0;
+		virtual ~EngineBase() {}
+		virtual int context_init(uint32_t n_max, uint32_t lambda, int64_t eps_num, uint32_t eps_den) = 0;
+		virtual int context_get(uint32_t* rho, uint32_t* mat) const = 0;
+		virtual int table_dim() const = 0;
+		virtual int block_dim(int sym) const = 0;
+		virtual int gblock_plan(int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S, const uint32_t* P) = 0;
+		virtual int gblock_run() = 0;
+		virtual int gblock_fetch(uint32_t* out) = 0;
+		virtual const uint32_t* device_tables() const = 0;
+		virtual int fblock_batch(int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
+		                         const int32_t* sym, uint32_t* out) = 0;
+	};
+	typedef EngineBase* (*EngineFactory)(int device, int prec);
+}  // namespace qb
+
+#ifdef QB_L
+// ------------------------------------------------------------------------------------------------------------------
+#include "hostmath.hpp"
+#include "kernels.cuh"
+
+namespace qb
+{
+	// grow-only device buffer
+	struct DevBuf
+	{
+		void* p = nullptr;
+		size_t cap = 0;
+		int ensure(size_t bytes)
+		{
+			if (bytes <= cap) return 0;
+			if (p) cudaFree(p);
+			p = nullptr;
+			cap = 0;
+			size_t want = bytes + bytes / 8 + 256;
+			if (cudaMalloc(&p, want) != cudaSuccess)
+			{
+				cudaGetLastError();
+				return -1;
+			}
+			cap = want;
+			return 0;
+		}
+		void release()
+		{
+			if (p) cudaFree(p);
+			p = nullptr;
+			cap = 0;
+		}
+		template <class T>
+		T* as() const
+		{
+			return static_cast<T*>(p);
+		}
+	};
+
+	template <int L>
+	struct Engine : EngineBase
+	{
+		using T = mpf<L>;
+		static constexpr int E = L + QB_EXT_LIMBS;
+		bool has_ctx = false;
+		uint32_t n_max = 0, lambda = 0;
+		Rational eps{0, 1};
+		ContextConsts<L> consts;
+		std::map<uint32_t, T> b0_cache;
+		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_fb_in, d_fb_v, d_fb_out, d_fb_terms;
+		DevCtx cx{};
+		int n_tables = 0, n_jobs = 0;
+		// layout of d_in: [delta | S | P] (tables) then spin; d_jobs: [delta | S | P | b0] (jobs) then spin
+		T *t_delta = nullptr, *t_S = nullptr, *t_P = nullptr;
+		uint32_t* t_spin = nullptr;
+		T *j_delta = nullptr, *j_S = nullptr, *j_P = nullptr, *j_b0 = nullptr;
+		uint32_t* j_spin = nullptr;
+
+		Engine(int dev, int prec_bits)
+		{
+			device = dev;
+			prec = prec_bits;
+			limbs = L;
+		}
+		~Engine() override
+		{
+			cudaSetDevice(device);
+			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_fb_in, &d_fb_v, &d_fb_out,
+			                  &d_fb_terms})
+				b->release();
+			if (stream) cudaStreamDestroy(stream);
+		}
+		int fail(cudaError_t e, const char* where)
+		{
+			cuda_error = std::string(where) + ": " + cudaGetErrorString(e);
+			cudaGetLastError();
+			return -5;
+		}
+#define QB_CU(call)                                    \
+	do                                                 \
+	{                                                  \
+		cudaError_t e_ = (call);                       \
+		if (e_ != cudaSuccess) return fail(e_, #call); \
+	} while (0)
+
+		int context_init(uint32_t nmax, uint32_t lam, int64_t en, uint32_t ed) override
+		{
+			if (ed == 0 || lam > 200 || nmax == 0) return -4;
+			QB_CU(cudaSetDevice(device));
+			n_max = nmax;
+			lambda = lam;
+			eps = Rational{en, ed};
+			make_context_consts<L>(consts, lam, prec);
+			b0_cache.clear();
+			// upload: rho | mat | kfact | ln2e | ln4e | lnrhoe
+			size_t n1 = size_t(lam) + 1;
+			size_t bytes = sizeof(T) * (1 + n1 * n1 + n1) + 3 * sizeof(mpf<E>);
+			if (d_consts.ensure(bytes)) return -7;
+			std::vector<uint8_t> host(bytes);
+			uint8_t* p = host.data();
+			auto put = [&](const void* src, size_t n) {
+				std::memcpy(p, src, n);
+				p += n;
+			};
+			put(&consts.rho, sizeof(T));
+			put(consts.mat.data(), sizeof(T) * n1 * n1);
+			put(consts.kfact.data(), sizeof(T) * n1);
+			put(&consts.ln2e, sizeof(mpf<E>));
+			put(&consts.ln4e, sizeof(mpf<E>));
+			put(&consts.lnrhoe, sizeof(mpf<E>));
+			QB_CU(cudaMemcpyAsync(d_consts.p, host.data(), bytes, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaStreamSynchronize(stream));
+			const uint8_t* d = d_consts.as<uint8_t>();
+			cx.prec = prec;
+			cx.n_max = nmax;
+			cx.lambda = lam;
+			cx.eps = eps;
+			cx.rho = reinterpret_cast<const uint32_t*>(d);
+			cx.mat = reinterpret_cast<const uint32_t*>(d + sizeof(T));
+			cx.kfact = reinterpret_cast<const uint32_t*>(d + sizeof(T) * (1 + n1 * n1));
+			const uint8_t* de = d + sizeof(T) * (1 + n1 * n1 + n1);
+			cx.ln2e = reinterpret_cast<const uint32_t*>(de);
+			cx.ln4e = reinterpret_cast<const uint32_t*>(de + sizeof(mpf<E>));
+			cx.lnrhoe = reinterpret_cast<const uint32_t*>(de + 2 * sizeof(mpf<E>));
+			has_ctx = true;
+			return 0;
+		}
+		int context_get(uint32_t* rho, uint32_t* mat) const override
+		{
+			if (!has_ctx) return -3;
+			if (rho) std::memcpy(rho, &consts.rho, sizeof(T));
+			if (mat) std::memcpy(mat, consts.mat.data(), sizeof(T) * consts.mat.size());
+			return 0;
+		}
+		int table_dim() const override { return has_ctx ? cf_dim(int(lambda)) : -3; }
+		int block_dim(int sym) const override { return has_ctx ? cf_dim_sym(int(lambda), sym) : -3; }
+
+		// b[0] = (-1)^spin (2 eps)_spin / (2^spin (eps)_spin), exact rational rounded once   (src/hor_recursion.cpp:17-19)
+		int leading_coefficient(T& out, uint32_t spin)
+		{
+			auto it = b0_cache.find(spin);
+			if (it != b0_cache.end())
+			{
+				out = it->second;
+				return 0;
+			}
+			constexpr int NB = 160;  // 5120-bit exact integers
+			if (spin > 400) return -6;
+			mpf<NB> num, den;
+			set_si(num, 1, 32 * NB);
+			set_si(den, 1, 32 * NB);
+			for (uint32_t i = 0; i < spin; ++i)
+			{
+				int64_t fn = 2 * eps.num + int64_t(i) * int64_t(eps.den);
+				int64_t fd = eps.num + int64_t(i) * int64_t(eps.den);
+				mul_si(num, num, fn, 32 * NB);
+				mul_si(den, den, 2 * fd, 32 * NB);
+				if ((kind(num) == K_REG && num.exp > 32 * NB - 64) || (kind(den) == K_REG && den.exp > 32 * NB - 64)) return -6;
+			}
+			if (is_zero(den)) return -6;
+			if (is_zero(num))
+				set_zero(out);
+			else
+				div_wide<L, NB>(out, num, den, prec);
+			if (spin & 1u) neg(out);
+			b0_cache[spin] = out;
+			return 0;
+		}
+		static bool positive_integer(const T& x) { return kind(x) == K_REG && !sign(x) && is_integer(x); }
+		// PrimaryOperator::is_divergent_hor (include/qboot/primary_op.hpp:68-77)
+		bool is_divergent(const T& D, uint32_t spin) const
+		{
+			T t, u;
+			si_sub(t, 1 - int64_t(spin), D, prec);
+			if (positive_integer(t)) return true;
+			mul_si(u, D, 2, prec);
+			sub_q(t, u, 2 * int64_t(eps.den) + 2 * eps.num, eps.den, prec);
+			neg(t);
+			if (positive_integer(t)) return true;
+			if (spin > 0)
+			{
+				sub_q(t, D, (1 + int64_t(spin)) * int64_t(eps.den) + 2 * eps.num, eps.den, prec);
+				neg(t);
+				if (positive_integer(t)) return true;
+			}
+			return false;
+		}
+
+		int gblock_plan(int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S, const uint32_t* P) override
+		{
+			if (!has_ctx) return -3;
+			if (n < 0 || (n > 0 && (!spin || !delta || !S || !P))) return -4;
+			QB_CU(cudaSetDevice(device));
+			const T* hd = reinterpret_cast<const T*>(delta);
+			const T* hS = reinterpret_cast<const T*>(S);
+			const T* hP = reinterpret_cast<const T*>(P);
+			std::vector<T> jd, jS, jP, jb;
+			std::vector<uint32_t> jsp;
+			std::vector<TableRef> tr(static_cast<size_t>(n));
+			jd.reserve(size_t(n));
+			jS.reserve(size_t(n));
+			jP.reserve(size_t(n));
+			jb.reserve(size_t(n));
+			jsp.reserve(size_t(n));
+			T small, onep, onem;
+			set_ui_2exp(small, 1, -(3 * prec) / 8 + 15, prec);  // 2^(-(3 prec)/8 + 15)          (hor_recursion.cpp:23)
+			add_si(onep, small, 1, prec);
+			neg(small);
+			add_si(onem, small, 1, prec);
+			for (int t = 0; t < n; ++t)
+			{
+				if ((hd[t].sk & 2u) || (hS[t].sk & 2u) || (hP[t].sk & 2u)) return -4;
+				T b0;
+				int rc = leading_coefficient(b0, spin[t]);
+				if (rc) return rc;
+				auto push = [&](const T& D) {
+					jd.push_back(D);
+					jS.push_back(hS[t]);
+					jP.push_back(hP[t]);
+					jb.push_back(b0);
+					jsp.push_back(spin[t]);
+					return int32_t(jd.size() - 1);
+				};
+				if (!is_zero(hd[t]) && is_divergent(hd[t], spin[t]))
+				{
+					// two evaluations at Delta (1 +- s), averaged                         (primary_op.hpp:53-56)
+					T dp, dm;
+					mul(dp, hd[t], onep, prec);
+					mul(dm, hd[t], onem, prec);
+					tr[size_t(t)].job0 = push(dp);
+					tr[size_t(t)].job1 = push(dm);
+				}
+				else
+				{
+					tr[size_t(t)].job0 = push(hd[t]);
+					tr[size_t(t)].job1 = -1;
+				}
+			}
+			n_tables = n;
+			n_jobs = int(jd.size());
+			if (n == 0) return 0;
+			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
+			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
+			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
+			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) ||
+			    d_g.ensure(sizeof(T) * dimM * nt))
+				return -7;
+			t_delta = d_in.as<T>();
+			t_S = t_delta + nt;
+			t_P = t_S + nt;
+			t_spin = reinterpret_cast<uint32_t*>(t_P + nt);
+			j_delta = d_jobs.as<T>();
+			j_S = j_delta + nj;
+			j_P = j_S + nj;
+			j_b0 = j_P + nj;
+			j_spin = reinterpret_cast<uint32_t*>(j_b0 + nj);
+			QB_CU(cudaMemcpyAsync(t_delta, hd, sizeof(T) * nt, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(t_S, hS, sizeof(T) * nt, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(t_P, hP, sizeof(T) * nt, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(t_spin, spin, 4 * nt, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(j_delta, jd.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(j_S, jS.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(j_P, jP.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(j_b0, jb.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(j_spin, jsp.data(), 4 * nj, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(d_tref.p, tr.data(), sizeof(TableRef) * nt, cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaStreamSynchronize(stream));  // host vectors go out of scope
+			return 0;
+		}
+
+		int gblock_run() override
+		{
+			if (!has_ctx) return -3;
+			if (n_tables == 0) return 0;
+			QB_CU(cudaSetDevice(device));
+			const int nk = int(lambda) + 1;
+			{
+				int threads = 128, total = n_jobs * QB_NCOEF;
+				k_rec_coeffs<L><<<(total + threads - 1) / threads, threads, 0, stream>>>(cx, n_jobs, j_delta, j_spin, j_S, j_P,
+				                                                                         d_coef.as<T>());
+				++launches;
+			}
+			{
+				int threads = 64;
+				k_series<L><<<(n_jobs + threads - 1) / threads, threads, 0, stream>>>(cx, n_jobs, j_delta, j_spin, j_b0,
+				                                                                      d_coef.as<T>(), d_b.as<T>());
+				++launches;
+			}
+			{
+				int G = 160 / nk;
+				if (G < 1) G = 1;
+				size_t smem = 2 * size_t(G) * nk * sizeof(T);
+				while (smem > 200 * 1024 && G > 1)
+				{
+					--G;
+					smem = 2 * size_t(G) * nk * sizeof(T);
+				}
+				if (smem > 48 * 1024)
+					QB_CU(cudaFuncSetAttribute(k_deriv<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+				int blocks = (n_tables + G - 1) / G;
+				k_deriv<L><<<blocks, G * nk, smem, stream>>>(cx, n_tables, G, d_tref.as<TableRef>(), t_delta, d_b.as<T>(),
+				                                             d_fr.as<T>());
+				++launches;
+			}
+			{
+				int threads = 64;
+				k_finish<L><<<(n_tables + threads - 1) / threads, threads, 0, stream>>>(cx, n_tables, t_delta, t_spin, t_S, t_P,
+				                                                                        d_fr.as<T>(), d_g.as<T>());
+				++launches;
+			}
+			QB_CU(cudaGetLastError());
+			return 0;
+		}
+		int gblock_fetch(uint32_t* out) override
+		{
+			if (!has_ctx) return -3;
+			if (n_tables == 0) return 0;
+			QB_CU(cudaSetDevice(device));
+			size_t bytes = sizeof(T) * size_t(cf_dim(int(lambda))) * size_t(n_tables);
+			QB_CU(cudaMemcpyAsync(out, d_g.p, bytes, cudaMemcpyDeviceToHost, stream));
+			QB_CU(cudaStreamSynchronize(stream));
+			return 0;
+		}
+		const uint32_t* device_tables() const override { return d_g.as<uint32_t>(); }
+
+		int fblock_batch(int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
+		                 const int32_t* sym, uint32_t* out) override
+		{
+			if (!has_ctx) return -3;
+			if (m < 0 || n_d < 0) return -4;
+			if (m == 0) return 0;
+			if (!table_idx || !d || !d_idx || !sym || !out || n_d == 0) return -4;
+			QB_CU(cudaSetDevice(device));
+			const int lam = int(lambda), dimM = cf_dim(lam);
+			const int dim_max = cf_dim_sym(lam, 0) > cf_dim_sym(lam, 1) ? cf_dim_sym(lam, 0) : cf_dim_sym(lam, 1);
+			std::vector<TermRef> terms(static_cast<size_t>(m));
+			int64_t ofs = 0;
+			for (int i = 0; i < m; ++i)
+			{
+				if (table_idx[i] < 0 || table_idx[i] >= n_tables || d_idx[i] < 0 || d_idx[i] >= n_d || (sym[i] != 0 && sym[i] != 1))
+					return -4;
+				terms[size_t(i)] = TermRef{table_idx[i], d_idx[i], sym[i], int32_t(ofs)};
+				ofs += cf_dim_sym(lam, sym[i]);
+				if (ofs > 0x7fffffff) return -4;
+			}
+			if (d_fb_in.ensure(sizeof(T) * size_t(n_d)) || d_fb_v.ensure(sizeof(T) * size_t(n_d) * size_t(dimM)) ||
+			    d_fb_out.ensure(sizeof(T) * size_t(ofs)) || d_fb_terms.ensure(sizeof(TermRef) * size_t(m)))
+				return -7;
+			QB_CU(cudaMemcpyAsync(d_fb_in.p, d, sizeof(T) * size_t(n_d), cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(d_fb_terms.p, terms.data(), sizeof(TermRef) * size_t(m), cudaMemcpyHostToDevice, stream));
+			{
+				int threads = 32;
+				k_vtod<L><<<(n_d + threads - 1) / threads, threads, 0, stream>>>(cx, n_d, d_fb_in.as<T>(), d_fb_v.as<T>());
+				++launches;
+			}
+			{
+				int threads = 128;
+				int64_t total = int64_t(m) * dim_max;
+				k_fblock<L><<<unsigned((total + threads - 1) / threads), threads, 0, stream>>>(
+				    cx, m, dim_max, d_fb_terms.as<TermRef>(), d_g.as<T>(), d_fb_v.as<T>(), d_fb_out.as<T>());
+				++launches;
+			}
+			QB_CU(cudaGetLastError());
+			QB_CU(cudaMemcpyAsync(out, d_fb_out.p, sizeof(T) * size_t(ofs), cudaMemcpyDeviceToHost, stream));
+			QB_CU(cudaStreamSynchronize(stream));
+			return 0;
+		}
+#undef QB_CU
+	};
+
+	template <int L>
+	EngineBase* make_engine(int device, int prec)
+	{
+		auto* e = new Engine<L>(device, prec);
+		if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+		{
+			cudaGetLastError();
+			delete e;
+			return nullptr;
+		}
+		return e;
+	}
+}  // namespace qb
+#endif  // QB_L

@@ -31,7 +31,7 @@ namespace qb
 
 	// value of one monomial |c| * Delta^a S^b P^c spin^d eps^e (sign handled by the caller unless `signed_c`)
 	template <int L>
-	QB_HD void hor_monomial(mpf<L>& t, const HorMono& mo, bool signed_c, const mpf<L>& D, const mpf<L>& S,
+	QB_HD QB_NOINLINE void hor_monomial(mpf<L>& t, const HorMono& mo, bool signed_c, const mpf<L>& D, const mpf<L>& S,
 	                        const mpf<L>& P, uint32_t spin, Rational eps, int prec)
 	{
 		int64_t c = mo.c;
@@ -83,7 +83,7 @@ namespace qb
 
 	// one coefficient a[i][d]
 	template <int L>
-	QB_HD void hor_coefficient(mpf<L>& r, const HorPoly& po, const HorMono* monos, const mpf<L>& D, const mpf<L>& S,
+	QB_HD QB_NOINLINE void hor_coefficient(mpf<L>& r, const HorPoly& po, const HorMono* monos, const mpf<L>& D, const mpf<L>& S,
 	                           const mpf<L>& P, uint32_t spin, Rational eps, int prec)
 	{
 		mpf<L> acc, t;
@@ -116,7 +116,7 @@ namespace qb
 
 	// c[0..m] (degree m) times (n + a)  ->  c[0..m+1]     (reference: Polynomial::_mul_linear, src/algebra/polynomial.cpp:76-83)
 	template <int L>
-	QB_HD void mul_linear(mpf<L>* c, int m, const mpf<L>& a, int prec)
+	QB_HD QB_NOINLINE void mul_linear(mpf<L>* c, int m, const mpf<L>& a, int prec)
 	{
 		// in place, top down: new[m+1] = c[m]; new[i] = c[i] * a + c[i-1]; new[0] = c[0] * a
 		copy(c[m + 1], c[m]);
@@ -127,7 +127,7 @@ namespace qb
 	// p_0 (first == true) or p_{K-1}: products of linear factors (n + a), built by repeated mul_linear exactly as the
 	// reference does (src/hor_formula.cpp:16-19,291-294 spin 0; :306-311,2049-2054 spin > 0).  p[0..deg].
 	template <int L>
-	QB_HD void rec_coeffs_end(mpf<L>* p, const mpf<L>& D, uint32_t spin, Rational eps, int prec, bool first)
+	QB_HD QB_NOINLINE void rec_coeffs_end(mpf<L>* p, const mpf<L>& D, uint32_t spin, Rational eps, int prec, bool first)
 	{
 		mpf<L> a;
 		if (spin == 0)
@@ -188,7 +188,7 @@ namespace qb
 
 	// All recurrence coefficients of one table: out[i * (deg + 1) + d], i < K, K = 6 / deg = 3 for spin 0, else 8 / 4.
 	template <int L>
-	QB_HD void rec_coeffs(mpf<L>* out, const mpf<L>& D, uint32_t spin, const mpf<L>& S, const mpf<L>& P, Rational eps,
+	QB_HD QB_NOINLINE void rec_coeffs(mpf<L>* out, const mpf<L>& D, uint32_t spin, const mpf<L>& S, const mpf<L>& P, Rational eps,
 	                      int prec, const HorPoly* polys, const HorMono* monos)
 	{
 		const int K = spin == 0 ? 6 : 8, deg = spin == 0 ? 3 : 4, st = deg + 1;
@@ -201,7 +201,7 @@ namespace qb
 
 	// p(n) by Horner with the integer n: s = s * n, s = s + c   (include/qboot/algebra/polynomial.hpp:66-83)
 	template <int L>
-	QB_HD void poly_eval_ui(mpf<L>& s, const mpf<L>* c, int deg, uint32_t n, int prec)
+	QB_HD QB_NOINLINE void poly_eval_ui(mpf<L>& s, const mpf<L>* c, int deg, uint32_t n, int prec)
 	{
 		copy(s, c[deg]);
 		for (int d = deg - 1; d >= 0; --d)
@@ -213,7 +213,7 @@ namespace qb
 
 	// b[0] .. b[n_max] of one table, b[0] given.  `coef` from rec_coeffs.  b is addressed as b[n * stride].
 	template <int L>
-	QB_HD void series(mpf<L>* b, int64_t stride, uint32_t n_max, const mpf<L>* coef, uint32_t spin, int prec)
+	QB_HD QB_NOINLINE void series(mpf<L>* b, int64_t stride, uint32_t n_max, const mpf<L>* coef, uint32_t spin, int prec)
 	{
 		const int K = spin == 0 ? 6 : 8, deg = spin == 0 ? 3 : 4, st = deg + 1;
 		mpf<L> sum, pv;

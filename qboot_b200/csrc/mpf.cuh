@@ -134,7 +134,7 @@ namespace qb
 	// (X = N little-endian limbs, any normalisation) to `prec` bits, nearest-even, into r.  X == 0 with sticky == 0
 	// gives +0 (MPFR: exact cancellation yields +0 under RNDN).
 	template <int L, int N>
-	QB_HD void round_to(mpf<L>& r, uint32_t sgn, int32_t e, const uint32_t* X, uint32_t sticky, int prec)
+	QB_HD QB_NOINLINE void round_to(mpf<L>& r, uint32_t sgn, int32_t e, const uint32_t* X, uint32_t sticky, int prec)
 	{
 		int t = N - 1;
 		while (t >= 0 && X[t] == 0u) --t;
@@ -208,34 +208,42 @@ namespace qb
 	}
 
 	// ---- limb products ---------------------------------------------------------------------------------------------
-	// out[0 .. NA+NB) = a[0..NA) * b[0..NB), product scanning with a 96-bit column accumulator
+	// out[0 .. NA+NB) = a[0..NA) * b[0..NB).  Operand scanning: one rolled loop over the limbs of a, the inner loop over b
+	// unrolled with b and a sliding NB-limb accumulator window held in registers (mad.wide.u32 + 64-bit add per limb
+	// product); after row i the lowest window limb is final and is stored.  Keeps the code a few hundred instructions.
 	template <int NA, int NB>
 	QB_HD QB_INLINE void mul_limbs(uint32_t* out, const uint32_t* a, const uint32_t* b)
 	{
-		uint64_t acc = 0;
-		uint32_t top = 0;
+		uint32_t rb[NB], acc[NB];
 #pragma unroll
-		for (int k = 0; k < NA + NB - 1; ++k)
+		for (int j = 0; j < NB; ++j)
 		{
-#pragma unroll
-			for (int i = 0; i < NA; ++i)
-			{
-				int j = k - i;
-				if (j < 0 || j >= NB) continue;
-				uint64_t p = uint64_t(a[i]) * uint64_t(b[j]);
-				acc += p;
-				top += (acc < p) ? 1u : 0u;
-			}
-			out[k] = uint32_t(acc);
-			acc = (acc >> 32) | (uint64_t(top) << 32);
-			top = 0;
+			rb[j] = b[j];
+			acc[j] = 0u;
 		}
-		out[NA + NB - 1] = uint32_t(acc);
+#pragma unroll 1
+		for (int i = 0; i < NA; ++i)
+		{
+			const uint32_t ai = a[i];
+			uint64_t t = uint64_t(ai) * rb[0] + acc[0];
+			out[i] = uint32_t(t);
+			uint32_t carry = uint32_t(t >> 32);
+#pragma unroll
+			for (int j = 1; j < NB; ++j)
+			{
+				t = uint64_t(ai) * rb[j] + acc[j] + carry;
+				acc[j - 1] = uint32_t(t);
+				carry = uint32_t(t >> 32);
+			}
+			acc[NB - 1] = carry;
+		}
+#pragma unroll
+		for (int j = 0; j < NB; ++j) out[NA + j] = acc[j];
 	}
 
 	// r = RN(a * b)
 	template <int L>
-	QB_HD void mul(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec)
+	QB_HD QB_NOINLINE void mul(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec)
 	{
 		uint32_t sgn = (a.sk ^ b.sk) & SIGN_BIT;
 		if (((a.sk | b.sk) & 2u) != 0u)
@@ -268,7 +276,7 @@ namespace qb
 	// out (N+1 limbs, extra limb at the bottom) and the returned sticky describe  sa*A*2^ea + sb*B*2^eb  exactly:
 	// value = (-1)^osgn * (OUT + sticky') * 2^(oe - 32(N+1)).  Returns false when the result is exactly zero.
 	template <int N>
-	QB_HD bool add_core(uint32_t* OUT, uint32_t& osgn, int32_t& oe, uint32_t& ostk, uint32_t sa, int32_t ea,
+	QB_HD QB_NOINLINE bool add_core(uint32_t* OUT, uint32_t& osgn, int32_t& oe, uint32_t& ostk, uint32_t sa, int32_t ea,
 	                    const uint32_t* A, uint32_t sb, int32_t eb, const uint32_t* B)
 	{
 		// order by magnitude so that |A*2^ea| >= |B*2^eb|
@@ -396,7 +404,7 @@ namespace qb
 
 	// r = RN(a + b) (negate_b: a - b)
 	template <int L>
-	QB_HD void add(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec, bool negate_b = false)
+	QB_HD QB_NOINLINE void add(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec, bool negate_b = false)
 	{
 		uint32_t sbk = negate_b ? (b.sk ^ SIGN_BIT) : b.sk;
 		if (((a.sk | b.sk) & 2u) != 0u)
@@ -451,7 +459,7 @@ namespace qb
 
 	// r = RN(a * b + c)   (mpfr_fma)
 	template <int L>
-	QB_HD void fma(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, const mpf<L>& c, int prec)
+	QB_HD QB_NOINLINE void fma(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, const mpf<L>& c, int prec)
 	{
 		if (((a.sk | b.sk | c.sk) & 2u) != 0u)
 		{
@@ -509,7 +517,7 @@ namespace qb
 	// ---- integer operands ------------------------------------------------------------------------------------------
 	// r = exact integer (must fit: |v| < 2^64 <= 2^prec)
 	template <int L>
-	QB_HD void set_si(mpf<L>& r, int64_t v, int prec)
+	QB_HD QB_NOINLINE void set_si(mpf<L>& r, int64_t v, int prec)
 	{
 		if (v == 0)
 		{
@@ -522,7 +530,7 @@ namespace qb
 		round_to<L, 2>(r, sgn, 64, X, 0u, prec);
 	}
 	template <int L>
-	QB_HD void set_ui_2exp(mpf<L>& r, uint64_t u, int32_t e, int prec)
+	QB_HD QB_NOINLINE void set_ui_2exp(mpf<L>& r, uint64_t u, int32_t e, int prec)
 	{
 		if (u == 0)
 		{
@@ -534,7 +542,7 @@ namespace qb
 	}
 	// r = RN(a * v)  (mpfr_mul_si / mpfr_mul_ui)
 	template <int L>
-	QB_HD void mul_si(mpf<L>& r, const mpf<L>& a, int64_t v, int prec)
+	QB_HD QB_NOINLINE void mul_si(mpf<L>& r, const mpf<L>& a, int64_t v, int prec)
 	{
 		uint32_t vs = v < 0 ? SIGN_BIT : 0u;
 		uint64_t u = v < 0 ? uint64_t(0) - uint64_t(v) : uint64_t(v);
@@ -577,7 +585,7 @@ namespace qb
 	}
 	// r = RN(a + v)
 	template <int L>
-	QB_HD void add_si(mpf<L>& r, const mpf<L>& a, int64_t v, int prec)
+	QB_HD QB_NOINLINE void add_si(mpf<L>& r, const mpf<L>& a, int64_t v, int prec)
 	{
 		if (v == 0)
 		{
@@ -591,7 +599,7 @@ namespace qb
 	}
 	// r = RN(v - a)
 	template <int L>
-	QB_HD void si_sub(mpf<L>& r, int64_t v, const mpf<L>& a, int prec)
+	QB_HD QB_NOINLINE void si_sub(mpf<L>& r, int64_t v, const mpf<L>& a, int prec)
 	{
 		if (v == 0)
 		{
@@ -636,7 +644,7 @@ namespace qb
 	}
 	// r = RN(a / v)  (mpfr_div_si / mpfr_div_ui), |v| < 2^32
 	template <int L>
-	QB_HD void div_si(mpf<L>& r, const mpf<L>& a, int64_t v, int prec)
+	QB_HD QB_NOINLINE void div_si(mpf<L>& r, const mpf<L>& a, int64_t v, int prec)
 	{
 		uint32_t vs = v < 0 ? SIGN_BIT : 0u;
 		uint64_t u = v < 0 ? uint64_t(0) - uint64_t(v) : uint64_t(v);
@@ -673,7 +681,7 @@ namespace qb
 	// ---- rational operands (num / den, |num| < 2^63, 0 < den < 2^32) --------------------------------------------------
 	// r = RN(num / den)  (mpfr_set_q)
 	template <int L>
-	QB_HD void set_q(mpf<L>& r, int64_t num, uint32_t den, int prec)
+	QB_HD QB_NOINLINE void set_q(mpf<L>& r, int64_t num, uint32_t den, int prec)
 	{
 		if (num == 0)
 		{
@@ -691,7 +699,7 @@ namespace qb
 	}
 	// r = RN(a * num / den)  (mpfr_mul_q: one rounding)
 	template <int L>
-	QB_HD void mul_q(mpf<L>& r, const mpf<L>& a, int64_t num, uint32_t den, int prec)
+	QB_HD QB_NOINLINE void mul_q(mpf<L>& r, const mpf<L>& a, int64_t num, uint32_t den, int prec)
 	{
 		uint32_t ns = num < 0 ? SIGN_BIT : 0u;
 		uint64_t u = num < 0 ? uint64_t(0) - uint64_t(num) : uint64_t(num);
@@ -720,7 +728,7 @@ namespace qb
 	}
 	// r = RN(a / (num / den)) = RN(a * den / num)  (mpfr_div_q), |num| < 2^32
 	template <int L>
-	QB_HD void div_q(mpf<L>& r, const mpf<L>& a, int64_t num, uint32_t den, int prec)
+	QB_HD QB_NOINLINE void div_q(mpf<L>& r, const mpf<L>& a, int64_t num, uint32_t den, int prec)
 	{
 		uint32_t ns = num < 0 ? SIGN_BIT : 0u;
 		uint64_t u = num < 0 ? uint64_t(0) - uint64_t(num) : uint64_t(num);
@@ -763,7 +771,7 @@ namespace qb
 	// exact inside a 2L-limb window; the quotient by den < 2^32 of such a numerator cannot sit within 2^-(32L) of a
 	// rounding boundary unless it is exact, so one rounding of the windowed value is the correct rounding.
 	template <int L>
-	QB_HD void add_q(mpf<L>& r, const mpf<L>& a, int64_t num, uint32_t den, int prec)
+	QB_HD QB_NOINLINE void add_q(mpf<L>& r, const mpf<L>& a, int64_t num, uint32_t den, int prec)
 	{
 		if (is_special(a))
 		{
@@ -838,7 +846,7 @@ namespace qb
 	// ---- division --------------------------------------------------------------------------------------------------
 	// r = RN(a / b): schoolbook long division (Knuth D) producing L+1 quotient limbs and a remainder-nonzero sticky
 	template <int L>
-	QB_HD void div(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec)
+	QB_HD QB_NOINLINE void div(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec)
 	{
 		uint32_t sgn = (a.sk ^ b.sk) & SIGN_BIT;
 		if (((a.sk | b.sk) & 2u) != 0u)
@@ -954,7 +962,7 @@ namespace qb
 	// ---- comparison / predicates -----------------------------------------------------------------------------------
 	// sign of a - b for zero/regular operands
 	template <int L>
-	QB_HD int cmp(const mpf<L>& a, const mpf<L>& b)
+	QB_HD QB_NOINLINE int cmp(const mpf<L>& a, const mpf<L>& b)
 	{
 		int sa = is_zero(a) ? 0 : (sign(a) ? -1 : 1);
 		int sb = is_zero(b) ? 0 : (sign(b) ? -1 : 1);
@@ -974,7 +982,7 @@ namespace qb
 	}
 	// mpfr_integer_p
 	template <int L>
-	QB_HD bool is_integer(const mpf<L>& a)
+	QB_HD QB_NOINLINE bool is_integer(const mpf<L>& a)
 	{
 		if (is_zero(a)) return true;
 		if (kind(a) != K_REG) return false;

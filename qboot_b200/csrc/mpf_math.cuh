@@ -62,7 +62,7 @@ namespace qb
 
 	// r = exp(t), all in E limbs at 32E bits.  ln2 = ln 2 at the same width.
 	template <int E>
-	QB_HD void exp_ext(mpf<E>& r, const mpf<E>& t, const mpf<E>& ln2)
+	QB_HD QB_NOINLINE void exp_ext(mpf<E>& r, const mpf<E>& t, const mpf<E>& ln2)
 	{
 		const int pe = 32 * E;
 		if (is_zero(t))
@@ -102,7 +102,7 @@ namespace qb
 
 	// r = RN_prec(exp(y * lnx)),  lnx and ln2 given in E = L + QB_EXT_LIMBS limbs
 	template <int L>
-	QB_HD void pow_from_log(mpf<L>& r, const mpf<L + QB_EXT_LIMBS>& lnx, const mpf<L>& y,
+	QB_HD QB_NOINLINE void pow_from_log(mpf<L>& r, const mpf<L + QB_EXT_LIMBS>& lnx, const mpf<L>& y,
 	                        const mpf<L + QB_EXT_LIMBS>& ln2, int prec)
 	{
 		constexpr int E = L + QB_EXT_LIMBS;

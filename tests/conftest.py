@@ -1,0 +1,40 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def hostemu():
+    """Host build of the engine's __host__ __device__ arithmetic (test harness only, tests/hostemu)."""
+    import ctypes
+
+    out = os.path.join(ROOT, "tests", "_build", "libqb_hostemu.so")
+    srcs = [os.path.join(ROOT, "tests", "hostemu", f) for f in ("hostemu_ops.cpp", "hostemu_block.cpp")]
+    deps = srcs + [os.path.join(ROOT, "qboot_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "qboot_b200", "csrc"))]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", out, *srcs])
+    return ctypes.CDLL(out)
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference (oracle/_ref); built on demand where /root/reference exists."""
+    from oracle import ref as r
+
+    if not r.available():
+        if os.path.isdir("/root/reference/src"):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "-j8"])
+        else:
+            pytest.skip("oracle/_ref not built and /root/reference absent")
+    return r
