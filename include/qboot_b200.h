@@ -96,6 +96,14 @@ uint64_t qb_stream(const qb_handle* h);
 int qb_fblock_batch(qb_handle* h, int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
                     const int32_t* sym, uint32_t* out);
 
+/* Diagnostic: one arithmetic primitive applied elementwise on the device (n records per operand, HOST memory; unused
+ * operands may be NULL).  op: 0 add, 1 sub, 2 mul, 3 div, 4 fma(a*b+c), 6 mul_si(a*ia), 7 add_si, 8 div_si, 9 mul_q
+ * (a*ia/ib), 10 div_q, 11 add_q, 12 set_q(ia/ib), 13 rho^b, 14 4^a, 18 si_sub(ia-a), 20 sub_q, 23 cmp(a,b)+1 in word 0,
+ * 24 is_integer(a) in word 0.  These are the mpfr_* calls of include/qboot/mp/real.hpp:324-361,767-786 that the table
+ * path uses; the entry exists so that the device build of each can be pinned against MPFR.  Needs a context. */
+int qb_op_batch(qb_handle* h, int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c,
+                const int64_t* ia, const int64_t* ib, uint32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ SYMBOLS = (
     "qb_version", "qb_strerror", "qb_precision_supported", "qb_create", "qb_destroy", "qb_words",
     "qb_last_cuda_error", "qb_context_init", "qb_context_get", "qb_table_dim", "qb_block_dim", "qb_gblock_batch",
     "qb_gblock_plan", "qb_gblock_run", "qb_gblock_fetch", "qb_sync", "qb_gblock_device_tables", "qb_launch_count",
-    "qb_stream", "qb_fblock_batch",
+    "qb_stream", "qb_fblock_batch", "qb_op_batch",
 )
 
 
@@ -64,6 +64,7 @@ def load_library():
     lib.qb_stream.restype = C.c_uint64
     lib.qb_fblock_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]
+    lib.qb_op_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
     _lib = lib
     return lib
 
@@ -233,6 +234,16 @@ class Engine:
             res.append(out[o:o + k])
             o += k
         return res
+
+    def op(self, code: int, a=None, b=None, c=None, ia=None, ib=None) -> np.ndarray:
+        """Diagnostic: one arithmetic primitive elementwise on the device (qb_op_batch)."""
+        arrs = [None if x is None else np.ascontiguousarray(x, dtype=np.uint32).reshape(-1, self.W) for x in (a, b, c)]
+        ints = [None if x is None else np.ascontiguousarray(x, dtype=np.int64).reshape(-1) for x in (ia, ib)]
+        n = next(len(x) for x in arrs + ints if x is not None)
+        out = np.zeros((n, self.W), dtype=np.uint32)
+        self._check(self.lib.qb_op_batch(self.h, int(code), n, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
+                                         _ptr(ints[0]), _ptr(ints[1]), _ptr(out)), "qb_op_batch")
+        return out
 
     @property
     def launches(self) -> int:

@@ -11,6 +11,8 @@
 //                      ComplexFunction mul / proj, include/qboot/algebra/complex_function.hpp:190-206)
 //
 // Every function performs the reference's operations in the reference's order, each rounded at `prec` bits.
+// Staging rule as in hor.cuh: arithmetic only on thread-local records; tables in global memory are read with copy()
+// into locals and written with copy() from locals.
 #pragma once
 
 #include "hor.cuh"
@@ -32,8 +34,8 @@ namespace qb
 		return h * (h + 1) / 2;
 	}
 
-	// ---- rho-derivatives ---------------------------------------------------------------------------------------------
-	// level-k scaling of one coefficient: a <- a * (q + n)          (derivate, real_function.hpp:236-240)
+	// ---- rho-derivatives (all operands thread-local) -----------------------------------------------------------------
+	// level-k scaling of one coefficient: a <- a_prev * (q + n)      (derivate, real_function.hpp:236-240)
 	template <int L>
 	QB_HD QB_INLINE void deriv_scale(mpf<L>& a, const mpf<L>& a_prev, const mpf<L>& q, uint32_t n, int prec)
 	{
@@ -49,27 +51,35 @@ namespace qb
 	}
 	// f_k = s * rho^q / k!                                           (real_function.hpp:262, hor_recursion.cpp:46-53)
 	template <int L>
-	QB_HD QB_NOINLINE void deriv_finish(mpf<L>& f, const mpf<L>& s, const mpf<L>& rho_pow_q, const mpf<L>& kfact, uint32_t k, int prec)
+	QB_HD QB_INLINE void deriv_finish(mpf<L>& f, const mpf<L>& s, const mpf<L>& rho_pow_q, const mpf<L>& kfact, uint32_t k,
+	                                  int prec)
 	{
 		mul(f, s, rho_pow_q, prec);
 		if (k >= 1) div(f, f, kfact, prec);
 	}
 
-	// z[i] = x[0] * M[0][i], then += x[j] * M[j][i]                  (dot, matrix.hpp:444-456); M row-major (lambda+1)^2
+	// z = x[0] * M[0][i], then += x[j] * M[j][i]   (dot, matrix.hpp:444-456); x, M anywhere; M row-major (lambda+1)^2;
+	// z thread-local
 	template <int L>
-	QB_HD QB_NOINLINE void rho_to_z_entry(mpf<L>& z, const mpf<L>* x, int64_t xstride, const mpf<L>* M, int lambda, int i, int prec)
+	QB_HD QB_NOINLINE void rho_to_z_entry(mpf<L>& z, const mpf<L>* x, int64_t xstride, const mpf<L>* M, int lambda, int i,
+	                                      int prec)
 	{
-		mpf<L> t;
-		mul(z, x[0], M[i], prec);
+		mpf<L> t, xv, mv;
+		copy(xv, x[0]);
+		copy(mv, M[i]);
+		mul(z, xv, mv, prec);
 		for (int j = 1; j <= lambda; ++j)
 		{
-			mul(t, x[int64_t(j) * xstride], M[j * (lambda + 1) + i], prec);
+			copy(xv, x[int64_t(j) * xstride]);
+			copy(mv, M[j * (lambda + 1) + i]);
+			mul(t, xv, mv, prec);
 			add(z, z, t, prec);
 		}
 	}
 
 	// ---- transverse recursion ------------------------------------------------------------------------------------------
 	// quad_casimir4 = 4 * ((2 eps + spin) spin / 2 + (Delta / 2 - eps - 1) Delta)    (primary_op.hpp:60-63, context.cpp:70)
+	// r, D thread-local
 	template <int L>
 	QB_HD QB_NOINLINE void quad_casimir4(mpf<L>& r, const mpf<L>& D, uint32_t spin, Rational eps, int prec)
 	{
@@ -86,21 +96,24 @@ namespace qb
 	}
 
 	// One row entry of the recursion: everything except the same-row correction, i.e. val / common_factor.
-	// f is the Mixed table (packed), rows n-1 and n-2 must be complete.                         (context.cpp:72-121)
+	// f is the Mixed table (packed, anywhere), rows n-1 and n-2 must be complete; val, S, P, qc4 thread-local.
+	// (context.cpp:72-121)
 	template <int L>
 	QB_HD QB_NOINLINE void offdiag_val(mpf<L>& val, const mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& S,
-	                       const mpf<L>& P, const mpf<L>& qc4, Rational eps, int prec)
+	                                   const mpf<L>& P, const mpf<L>& qc4, Rational eps, int prec)
 	{
-		mpf<L> term, t2;
-#define QB_F(mm, nn) f[int64_t(cf_index(lambda, (mm), (nn))) * fs]
+		mpf<L> term, t2, h;
+#define QB_LOADF(mm, nn) copy(h, f[int64_t(cf_index(lambda, (mm), (nn))) * fs])
 		// h[m + 2, n - 1]
-		mul_si(val, QB_F(m + 2, n - 1), -int64_t(m + 1) * (m + 2), prec);
+		QB_LOADF(m + 2, n - 1);
+		mul_si(val, h, -int64_t(m + 1) * (m + 2), prec);
 		// h[m + 1, n - 1]
 		add_q(term, S, eps.num, eps.den, prec);
 		mul_si(term, term, 2, prec);
 		add_si(term, term, -int64_t(m + 4 * n - 6), prec);
 		mul_si(term, term, 2 * (m + 1), prec);
-		mul(term, term, QB_F(m + 1, n - 1), prec);
+		QB_LOADF(m + 1, n - 1);
+		mul(term, term, h, prec);
 		add(val, val, term, prec);
 		// h[m, n - 1]
 		set_q(term, eps.num * int64_t(4 * (m + n - 1)), eps.den, prec);
@@ -111,7 +124,8 @@ namespace qb
 		add(term, term, t2, prec);
 		add(term, term, qc4, prec);
 		mul_si(term, term, 4, prec);
-		mul(term, term, QB_F(m, n - 1), prec);
+		QB_LOADF(m, n - 1);
+		mul(term, term, h, prec);
 		add(val, val, term, prec);
 		// h[m - 1, n - 1]
 		if (m >= 1)
@@ -123,7 +137,8 @@ namespace qb
 			mul_si(t2, S, int64_t(8 * n + 2 * m - 10), prec);
 			add(term, term, t2, prec);
 			mul_si(term, term, 8, prec);
-			mul(term, term, QB_F(m - 1, n - 1), prec);
+			QB_LOADF(m - 1, n - 1);
+			mul(term, term, h, prec);
 			add(val, val, term, prec);
 		}
 		// h[m + 1, n - 2] and h[m + 2, n - 2]
@@ -134,95 +149,118 @@ namespace qb
 			mul_si(t2, S, 2, prec);
 			add(term, term, t2, prec);
 			mul_si(term, term, int64_t(8 * (m + 1)), prec);
-			mul(term, term, QB_F(m + 1, n - 2), prec);
-			mul_si(t2, QB_F(m + 2, n - 2), int64_t(4 * (m + 1) * (m + 2)), prec);
+			QB_LOADF(m + 1, n - 2);
+			mul(term, term, h, prec);
+			QB_LOADF(m + 2, n - 2);
+			mul_si(t2, h, int64_t(4 * (m + 1) * (m + 2)), prec);
 			add(term, term, t2, prec);
 			add(val, val, term, prec);
 		}
-#undef QB_F
+#undef QB_LOADF
 		// common_factor = 4 n eps + (4 n - 2) n
 		int64_t cn = int64_t(4 * n) * eps.num + int64_t(4 * n - 2) * int64_t(n) * int64_t(eps.den);
 		div_q(val, val, cn, eps.den, prec);
 	}
-	// h[m, n] = val + 8 h[m-3, n] + 4 h[m-2, n] - 2 h[m-1, n]                                  (context.cpp:123-130)
+	// h[m, n] = val + 8 h[m-3, n] + 4 h[m-2, n] - 2 h[m-1, n]; the three predecessors are handed in thread-local
+	// (p1 = h[m-1,n], p2 = h[m-2,n], p3 = h[m-3,n]); result thread-local                          (context.cpp:123-130)
 	template <int L>
-	QB_HD QB_NOINLINE void offdiag_close(mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& val, int prec)
+	QB_HD QB_NOINLINE void offdiag_close(mpf<L>& out, int m, const mpf<L>& val, const mpf<L>& p1, const mpf<L>& p2,
+	                                     const mpf<L>& p3, int prec)
 	{
 		mpf<L> term, t2;
 		set_zero(term);
 		if (m >= 3)
 		{
-			mul_si(t2, f[int64_t(cf_index(lambda, m - 3, n)) * fs], 8, prec);
+			mul_si(t2, p3, 8, prec);
 			add(term, term, t2, prec);
 		}
 		if (m >= 2)
 		{
-			mul_si(t2, f[int64_t(cf_index(lambda, m - 2, n)) * fs], 4, prec);
+			mul_si(t2, p2, 4, prec);
 			add(term, term, t2, prec);
 		}
 		if (m >= 1)
 		{
-			mul_si(t2, f[int64_t(cf_index(lambda, m - 1, n)) * fs], 2, prec);
+			mul_si(t2, p1, 2, prec);
 			sub(term, term, t2, prec);
 		}
-		add(f[int64_t(cf_index(lambda, m, n)) * fs], val, term, prec);
+		add(out, val, term, prec);
 	}
-	// whole table, serial: f row 0 (dx = 0..lambda) must be filled
+	// whole table, serial: f (anywhere) row 0 (dx = 0..lambda) must be filled; D, S, P anywhere
 	template <int L>
-	QB_HD QB_NOINLINE void expand_off_diag(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& D, uint32_t spin, const mpf<L>& S,
-	                           const mpf<L>& P, Rational eps, int prec)
+	QB_HD void expand_off_diag(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& Din, uint32_t spin, const mpf<L>& Sin,
+	                           const mpf<L>& Pin, Rational eps, int prec)
 	{
-		mpf<L> qc4, val;
+		mpf<L> D, S, P, qc4, val, p1, p2, p3, cur;
+		copy(D, Din);
+		copy(S, Sin);
+		copy(P, Pin);
 		quad_casimir4(qc4, D, spin, eps, prec);
 		for (int n = 1; n <= lambda / 2; ++n)
+		{
+			set_zero(p1);
+			set_zero(p2);
+			set_zero(p3);
 			for (int m = 0; m + 2 * n <= lambda; ++m)
 			{
 				offdiag_val(val, f, fs, lambda, m, n, S, P, qc4, eps, prec);
-				offdiag_close(f, fs, lambda, m, n, val, prec);
+				offdiag_close(cur, m, val, p1, p2, p3, prec);
+				copy(f[int64_t(cf_index(lambda, m, n)) * fs], cur);
+				copy(p3, p2);
+				copy(p2, p1);
+				copy(p1, cur);
 			}
+		}
 	}
 
 	// ---- v^d table -------------------------------------------------------------------------------------------------------
 	// f(0,0) = 4^-d given (pow); f(0,n) = f(0,n-1) * 4 * (-d + (n-1)) / n; f(m,n) = f(m-1,n) * (-4 d + 2 (m+2n-1)) / m
+	// f anywhere; d, four_pow_minus_d anywhere
 	template <int L>
-	QB_HD QB_NOINLINE void v_to_d_table(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& d, const mpf<L>& four_pow_minus_d, int prec)
+	QB_HD void v_to_d_table(mpf<L>* f, int64_t fs, int lambda, const mpf<L>& din, const mpf<L>& four_pow_minus_d, int prec)
 	{
-		mpf<L> md, t, u;
+		mpf<L> d, md, t, u, row0, cur;
+		copy(d, din);
 		copy(md, d);
 		neg(md);
-		copy(f[0], four_pow_minus_d);
+		copy(row0, four_pow_minus_d);
 		for (int n = 0; n <= lambda / 2; ++n)
 		{
 			if (n > 0)
 			{
-				mul_si(t, f[int64_t(cf_index(lambda, 0, n - 1)) * fs], 4, prec);
+				mul_si(t, row0, 4, prec);
 				add_si(u, md, int64_t(n - 1), prec);
 				mul(t, t, u, prec);
-				div_si(f[int64_t(cf_index(lambda, 0, n)) * fs], t, int64_t(n), prec);
+				div_si(row0, t, int64_t(n), prec);
 			}
+			copy(f[int64_t(cf_index(lambda, 0, n)) * fs], row0);
+			copy(cur, row0);
 			for (int m = 1; m + 2 * n <= lambda; ++m)
 			{
 				mul_si(u, d, -4, prec);
 				add_si(u, u, int64_t(2 * (m + 2 * n - 1)), prec);
-				mul(t, f[int64_t(cf_index(lambda, m - 1, n)) * fs], u, prec);
-				div_si(f[int64_t(cf_index(lambda, m, n)) * fs], t, int64_t(m), prec);
+				mul(t, cur, u, prec);
+				div_si(cur, t, int64_t(m), prec);
+				copy(f[int64_t(cf_index(lambda, m, n)) * fs], cur);
 			}
 		}
 	}
 
 	// ---- F / H block -------------------------------------------------------------------------------------------------------
-	// out = 2 * sum_{dy1 <= N} sum_{dx1 <= M} v(dx1, dy1) * g(M - dx1, N - dy1), accumulated in that order
+	// out = 2 * sum_{dy1 <= N} sum_{dx1 <= M} v(dx1, dy1) * g(M - dx1, N - dy1), accumulated in that order.
+	// v, g anywhere; out thread-local
 	template <int L>
-	QB_HD QB_NOINLINE void fblock_entry(mpf<L>& out, const mpf<L>* v, int64_t vs, const mpf<L>* g, int64_t gs, int lambda, int M, int N,
-	                        int prec)
+	QB_HD QB_NOINLINE void fblock_entry(mpf<L>& out, const mpf<L>* v, int64_t vs, const mpf<L>* g, int64_t gs, int lambda, int M,
+	                                    int N, int prec)
 	{
-		mpf<L> acc, t;
+		mpf<L> acc, t, a, b;
 		set_zero(acc);
 		for (int dy1 = 0; dy1 <= N; ++dy1)
 			for (int dx1 = 0; dx1 <= M; ++dx1)
 			{
-				// (dx1, dy1) must itself be a valid index: dx1 + 2 dy1 <= lambda holds since dx1 <= M, dy1 <= N, M + 2N <= lambda
-				mul(t, v[int64_t(cf_index(lambda, dx1, dy1)) * vs], g[int64_t(cf_index(lambda, M - dx1, N - dy1)) * gs], prec);
+				copy(a, v[int64_t(cf_index(lambda, dx1, dy1)) * vs]);
+				copy(b, g[int64_t(cf_index(lambda, M - dx1, N - dy1)) * gs]);
+				mul(t, a, b, prec);
 				add(acc, acc, t, prec);
 			}
 		mul_si(out, acc, 2, prec);

@@ -130,6 +130,11 @@ extern "C"
 		if (n > 0 && !out) return QB_ERR_BAD_ARG;
 		return h->e->gblock_fetch(out);
 	}
+	int qb_op_batch(qb_handle* h, int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c,
+	                const int64_t* ia, const int64_t* ib, uint32_t* out)
+	{
+		return h ? h->e->op_batch(op, n, a, b, c, ia, ib, out) : QB_ERR_BAD_ARG;
+	}
 	int qb_fblock_batch(qb_handle* h, int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
 	                    const int32_t* sym, uint32_t* out)
 	{

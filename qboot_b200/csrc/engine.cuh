@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -30,6 +31,8 @@ namespace qb
 		virtual const uint32_t* device_tables() const = 0;
 		virtual int fblock_batch(int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
 		                         const int32_t* sym, uint32_t* out) = 0;
+		virtual int op_batch(int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c, const int64_t* ia,
+		                     const int64_t* ib, uint32_t* out) = 0;
 	};
 	typedef EngineBase* (*EngineFactory)(int device, int prec);
 }  // namespace qb
@@ -106,6 +109,16 @@ namespace qb
 			                  &d_fb_terms})
 				b->release();
 			if (stream) cudaStreamDestroy(stream);
+		}
+		// QB_DEBUG_SYNC=1: synchronise after every kernel so that a fault is attributed to the kernel that raised it
+		int debug_sync(const char* kernel)
+		{
+			static const bool on = std::getenv("QB_DEBUG_SYNC") != nullptr;
+			if (!on) return 0;
+			cudaError_t e = cudaStreamSynchronize(stream);
+			if (e == cudaSuccess) e = cudaGetLastError();
+			if (e != cudaSuccess) return fail(e, kernel);
+			return 0;
 		}
 		int fail(cudaError_t e, const char* where)
 		{
@@ -316,12 +329,14 @@ namespace qb
 				k_rec_coeffs<L><<<(total + threads - 1) / threads, threads, 0, stream>>>(cx, n_jobs, j_delta, j_spin, j_S, j_P,
 				                                                                         d_coef.as<T>());
 				++launches;
+				if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
 			}
 			{
 				int threads = 64;
 				k_series<L><<<(n_jobs + threads - 1) / threads, threads, 0, stream>>>(cx, n_jobs, j_delta, j_spin, j_b0,
 				                                                                      d_coef.as<T>(), d_b.as<T>());
 				++launches;
+				if (int rc_ = debug_sync("k_series")) return rc_;
 			}
 			{
 				int G = 160 / nk;
@@ -338,12 +353,14 @@ namespace qb
 				k_deriv<L><<<blocks, G * nk, smem, stream>>>(cx, n_tables, G, d_tref.as<TableRef>(), t_delta, d_b.as<T>(),
 				                                             d_fr.as<T>());
 				++launches;
+				if (int rc_ = debug_sync("k_deriv")) return rc_;
 			}
 			{
 				int threads = 64;
 				k_finish<L><<<(n_tables + threads - 1) / threads, threads, 0, stream>>>(cx, n_tables, t_delta, t_spin, t_S, t_P,
 				                                                                        d_fr.as<T>(), d_g.as<T>());
 				++launches;
+				if (int rc_ = debug_sync("k_finish")) return rc_;
 			}
 			QB_CU(cudaGetLastError());
 			return 0;
@@ -389,6 +406,7 @@ namespace qb
 				int threads = 32;
 				k_vtod<L><<<(n_d + threads - 1) / threads, threads, 0, stream>>>(cx, n_d, d_fb_in.as<T>(), d_fb_v.as<T>());
 				++launches;
+				if (int rc_ = debug_sync("k_vtod")) return rc_;
 			}
 			{
 				int threads = 128;
@@ -396,9 +414,38 @@ namespace qb
 				k_fblock<L><<<unsigned((total + threads - 1) / threads), threads, 0, stream>>>(
 				    cx, m, dim_max, d_fb_terms.as<TermRef>(), d_g.as<T>(), d_fb_v.as<T>(), d_fb_out.as<T>());
 				++launches;
+				if (int rc_ = debug_sync("k_fblock")) return rc_;
 			}
 			QB_CU(cudaGetLastError());
 			QB_CU(cudaMemcpyAsync(out, d_fb_out.p, sizeof(T) * size_t(ofs), cudaMemcpyDeviceToHost, stream));
+			QB_CU(cudaStreamSynchronize(stream));
+			return 0;
+		}
+		int op_batch(int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c, const int64_t* ia,
+		             const int64_t* ib, uint32_t* out) override
+		{
+			if (!has_ctx) return -3;
+			if (n <= 0 || !out) return n == 0 ? 0 : -4;
+			QB_CU(cudaSetDevice(device));
+			const size_t rec = sizeof(T) * size_t(n), ints = 8 * size_t(n);
+			if (d_fb_in.ensure(4 * rec + 2 * ints)) return -7;
+			uint8_t* base = d_fb_in.as<uint8_t>();
+			T* da = reinterpret_cast<T*>(base);
+			T* db = reinterpret_cast<T*>(base + rec);
+			T* dc = reinterpret_cast<T*>(base + 2 * rec);
+			T* dout = reinterpret_cast<T*>(base + 3 * rec);
+			int64_t* dia = reinterpret_cast<int64_t*>(base + 4 * rec);
+			int64_t* dib = reinterpret_cast<int64_t*>(base + 4 * rec + ints);
+			if (a) QB_CU(cudaMemcpyAsync(da, a, rec, cudaMemcpyHostToDevice, stream));
+			if (b) QB_CU(cudaMemcpyAsync(db, b, rec, cudaMemcpyHostToDevice, stream));
+			if (c) QB_CU(cudaMemcpyAsync(dc, c, rec, cudaMemcpyHostToDevice, stream));
+			if (ia) QB_CU(cudaMemcpyAsync(dia, ia, ints, cudaMemcpyHostToDevice, stream));
+			if (ib) QB_CU(cudaMemcpyAsync(dib, ib, ints, cudaMemcpyHostToDevice, stream));
+			k_ops<L><<<(n + 63) / 64, 64, 0, stream>>>(cx, op, n, a ? da : nullptr, b ? db : nullptr, c ? dc : nullptr,
+			                                           ia ? dia : nullptr, ib ? dib : nullptr, dout);
+			++launches;
+			QB_CU(cudaGetLastError());
+			QB_CU(cudaMemcpyAsync(out, dout, rec, cudaMemcpyDeviceToHost, stream));
 			QB_CU(cudaStreamSynchronize(stream));
 			return 0;
 		}
@@ -409,6 +456,7 @@ namespace qb
 	EngineBase* make_engine(int device, int prec)
 	{
 		auto* e = new Engine<L>(device, prec);
+		if (const char* ss = std::getenv("QB_STACK_BYTES")) cudaDeviceSetLimit(cudaLimitStackSize, size_t(std::atol(ss)));
 		if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
 		{
 			cudaGetLastError();

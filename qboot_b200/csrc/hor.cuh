@@ -2,11 +2,15 @@
 //
 //   rec_coeffs   : coefficients of  sum_i p_i(n) b[n-i] = 0   (reference: _get_rec_coeffs, include/qboot/hor_formula.hpp:34-39,
 //                  src/hor_formula.cpp:8-296 spin 0, :298-2055 spin > 0)
-//   series_step  : b[n] = -(sum_{i=1}^{min(n,K-1)} p_i(n) b[n-i]) / p_0(n)   (src/hor_recursion.cpp:31-37)
+//   series       : b[n] = -(sum_{i=1}^{min(n,K-1)} p_i(n) b[n-i]) / p_0(n)   (src/hor_recursion.cpp:31-37)
 //
 // The middle polynomials p_1..p_{K-2} come from the integer tensors in hor_table.inc (tools/derive_hor_table.py);
 // each coefficient is evaluated monomial by monomial in lexicographic order, every product and every partial sum
 // rounded at `prec` bits, which reproduces the reference's MPFR evaluation bit for bit.
+//
+// Staging rule (device): the arithmetic routines of mpf.cuh are only ever handed thread-local records.  Operands that
+// live in global or shared memory are copied into locals first and results are copied out afterwards, so that every
+// limb routine addresses one memory space only.
 #pragma once
 
 #include "mpf.cuh"
@@ -29,10 +33,11 @@ namespace qb
 		uint32_t den;
 	};
 
-	// value of one monomial |c| * Delta^a S^b P^c spin^d eps^e (sign handled by the caller unless `signed_c`)
+	// value of one monomial |c| * Delta^a S^b P^c spin^d eps^e (sign handled by the caller unless `signed_c`);
+	// t, D, S, P are thread-local
 	template <int L>
-	QB_HD QB_NOINLINE void hor_monomial(mpf<L>& t, const HorMono& mo, bool signed_c, const mpf<L>& D, const mpf<L>& S,
-	                        const mpf<L>& P, uint32_t spin, Rational eps, int prec)
+	QB_HD QB_NOINLINE void hor_monomial(mpf<L>& t, HorMono mo, bool signed_c, const mpf<L>& D, const mpf<L>& S,
+	                                    const mpf<L>& P, uint32_t spin, Rational eps, int prec)
 	{
 		int64_t c = mo.c;
 		if (!signed_c && c < 0) c = -c;
@@ -81,10 +86,10 @@ namespace qb
 		for (; ne > 0; --ne) mul_q(t, t, eps.num, eps.den, prec);
 	}
 
-	// one coefficient a[i][d]
+	// one coefficient a[i][d]; r, D, S, P thread-local, the tables anywhere
 	template <int L>
-	QB_HD QB_NOINLINE void hor_coefficient(mpf<L>& r, const HorPoly& po, const HorMono* monos, const mpf<L>& D, const mpf<L>& S,
-	                           const mpf<L>& P, uint32_t spin, Rational eps, int prec)
+	QB_HD QB_NOINLINE void hor_coefficient(mpf<L>& r, HorPoly po, const HorMono* monos, const mpf<L>& D, const mpf<L>& S,
+	                                       const mpf<L>& P, uint32_t spin, Rational eps, int prec)
 	{
 		mpf<L> acc, t;
 		if (po.count == 0)
@@ -94,7 +99,7 @@ namespace qb
 			hor_monomial(acc, monos[po.first], true, D, S, P, spin, eps, prec);
 			for (int k = 1; k < po.count; ++k)
 			{
-				const HorMono& mo = monos[po.first + k];
+				HorMono mo = monos[po.first + k];
 				hor_monomial(t, mo, false, D, S, P, spin, eps, prec);
 				add(acc, acc, t, prec, mo.c < 0);
 			}
@@ -115,6 +120,7 @@ namespace qb
 	}
 
 	// c[0..m] (degree m) times (n + a)  ->  c[0..m+1]     (reference: Polynomial::_mul_linear, src/algebra/polynomial.cpp:76-83)
+	// c is a thread-local array
 	template <int L>
 	QB_HD QB_NOINLINE void mul_linear(mpf<L>* c, int m, const mpf<L>& a, int prec)
 	{
@@ -125,7 +131,7 @@ namespace qb
 	}
 
 	// p_0 (first == true) or p_{K-1}: products of linear factors (n + a), built by repeated mul_linear exactly as the
-	// reference does (src/hor_formula.cpp:16-19,291-294 spin 0; :306-311,2049-2054 spin > 0).  p[0..deg].
+	// reference does (src/hor_formula.cpp:16-19,291-294 spin 0; :306-311,2049-2054 spin > 0).  p[0..deg] thread-local.
 	template <int L>
 	QB_HD QB_NOINLINE void rec_coeffs_end(mpf<L>* p, const mpf<L>& D, uint32_t spin, Rational eps, int prec, bool first)
 	{
@@ -186,20 +192,30 @@ namespace qb
 		}
 	}
 
-	// All recurrence coefficients of one table: out[i * (deg + 1) + d], i < K, K = 6 / deg = 3 for spin 0, else 8 / 4.
+	// All recurrence coefficients of one table into out[i * (deg + 1) + d] (out anywhere), i < K,
+	// K = 6 / deg = 3 for spin 0, else 8 / 4.  Serial convenience used by the host harness.
 	template <int L>
-	QB_HD QB_NOINLINE void rec_coeffs(mpf<L>* out, const mpf<L>& D, uint32_t spin, const mpf<L>& S, const mpf<L>& P, Rational eps,
+	QB_HD void rec_coeffs(mpf<L>* out, const mpf<L>& Din, uint32_t spin, const mpf<L>& Sin, const mpf<L>& Pin, Rational eps,
 	                      int prec, const HorPoly* polys, const HorMono* monos)
 	{
 		const int K = spin == 0 ? 6 : 8, deg = spin == 0 ? 3 : 4, st = deg + 1;
+		mpf<L> D, S, P, r, pe[5];
+		copy(D, Din);
+		copy(S, Sin);
+		copy(P, Pin);
 		for (int i = 1; i < K - 1; ++i)
 			for (int d = 0; d <= deg; ++d)
-				hor_coefficient(out[i * st + d], polys[(i - 1) * st + d], monos, D, S, P, spin, eps, prec);
-		rec_coeffs_end(out, D, spin, eps, prec, true);
-		rec_coeffs_end(out + (K - 1) * st, D, spin, eps, prec, false);
+			{
+				hor_coefficient(r, polys[(i - 1) * st + d], monos, D, S, P, spin, eps, prec);
+				copy(out[i * st + d], r);
+			}
+		rec_coeffs_end(pe, D, spin, eps, prec, true);
+		for (int d = 0; d <= deg; ++d) copy(out[d], pe[d]);
+		rec_coeffs_end(pe, D, spin, eps, prec, false);
+		for (int d = 0; d <= deg; ++d) copy(out[(K - 1) * st + d], pe[d]);
 	}
 
-	// p(n) by Horner with the integer n: s = s * n, s = s + c   (include/qboot/algebra/polynomial.hpp:66-83)
+	// p(n) by Horner with the integer n: s = s * n, s = s + c   (include/qboot/algebra/polynomial.hpp:66-83); c thread-local
 	template <int L>
 	QB_HD QB_NOINLINE void poly_eval_ui(mpf<L>& s, const mpf<L>* c, int deg, uint32_t n, int prec)
 	{
@@ -211,24 +227,29 @@ namespace qb
 		}
 	}
 
-	// b[0] .. b[n_max] of one table, b[0] given.  `coef` from rec_coeffs.  b is addressed as b[n * stride].
+	// b[0] .. b[n_max] of one table, b[0] given (b anywhere, addressed as b[n * stride]); `coef` from rec_coeffs (anywhere).
+	// Coefficients and the last seven series terms are kept in thread-local storage.
 	template <int L>
-	QB_HD QB_NOINLINE void series(mpf<L>* b, int64_t stride, uint32_t n_max, const mpf<L>* coef, uint32_t spin, int prec)
+	QB_HD void series(mpf<L>* b, int64_t stride, uint32_t n_max, const mpf<L>* coef, uint32_t spin, int prec)
 	{
 		const int K = spin == 0 ? 6 : 8, deg = spin == 0 ? 3 : 4, st = deg + 1;
-		mpf<L> sum, pv;
+		mpf<L> lc[40], hist[8], sum, pv, bn;
+		for (int i = 0; i < K * st; ++i) copy(lc[i], coef[i]);
+		copy(hist[0], b[0]);
 		for (uint32_t n = 1; n <= n_max; ++n)
 		{
 			set_zero(sum);
 			for (int i = 1; i < K; ++i)
 				if (uint32_t(i) <= n)
 				{
-					poly_eval_ui(pv, coef + i * st, deg, n, prec);
-					fma(sum, pv, b[int64_t(n - uint32_t(i)) * stride], sum, prec);
+					poly_eval_ui(pv, lc + i * st, deg, n, prec);
+					fma(sum, pv, hist[(n - uint32_t(i)) & 7u], sum, prec);
 				}
 			neg(sum);
-			poly_eval_ui(pv, coef, deg, n, prec);
-			div(b[int64_t(n) * stride], sum, pv, prec);
+			poly_eval_ui(pv, lc, deg, n, prec);
+			div(bn, sum, pv, prec);
+			copy(hist[n & 7u], bn);
+			copy(b[int64_t(n) * stride], bn);
 		}
 	}
 }  // namespace qb

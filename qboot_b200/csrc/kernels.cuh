@@ -7,8 +7,11 @@
 //   k_finish       one thread per table: rho->z matrix and the transverse (Casimir) recursion        -> g[table][dim_M]
 //   k_vtod         one thread per distinct d: 4^-d and the v^d table
 //   k_fblock       one thread per (term, kept entry): 2 * proj(v^d * g)
+//   k_ops          diagnostic: one primitive elementwise
 //
 // Numbers are records of L + 2 words (mpf<L>), arrays of records in HBM.  Arithmetic: mpf.cuh / hor.cuh / block.cuh.
+// Staging rule: kernels copy operands from global / shared memory into thread-local records before any arithmetic
+// call and copy results back afterwards (see hor.cuh).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -19,7 +22,7 @@
 
 namespace qb
 {
-	// device-resident context constants (see qb_context_upload)
+	// device-resident context constants (see qb_context_init)
 	struct DevCtx
 	{
 		int prec;
@@ -56,14 +59,22 @@ namespace qb
 		mpf<L>* out = coef + size_t(job) * QB_NCOEF;
 		const HorPoly* polys = sp == 0 ? QB_HOR_POLY_0 : QB_HOR_POLY_1;
 		const HorMono* monos = sp == 0 ? QB_HOR_MONO_0 : QB_HOR_MONO_1;
+		mpf<L> lD, lS, lP;
+		copy(lD, delta[job]);
 		if (i >= 1 && i < K - 1)
 		{
-			hor_coefficient(out[c], polys[(i - 1) * st + d], monos, delta[job], S[job], P[job], sp, cx.eps, cx.prec);
+			mpf<L> r;
+			copy(lS, S[job]);
+			copy(lP, P[job]);
+			hor_coefficient(r, polys[(i - 1) * st + d], monos, lD, lS, lP, sp, cx.eps, cx.prec);
+			copy(out[c], r);
 			return;
 		}
 		// p_0 and p_{K-1}: products of linear factors; the d == 0 thread of each builds the whole polynomial
 		if (d != 0) return;
-		rec_coeffs_end(out + i * st, delta[job], sp, cx.eps, cx.prec, i == 0);
+		mpf<L> pe[5];
+		rec_coeffs_end(pe, lD, sp, cx.eps, cx.prec, i == 0);
+		for (int k = 0; k < st; ++k) copy(out[i * st + k], pe[k]);
 	}
 
 	template <int L>
@@ -96,17 +107,18 @@ namespace qb
 		const bool active = (g < G) && (t < n_tables);
 		mpf<L>* buf0 = reinterpret_cast<mpf<L>*>(smem_raw);
 		mpf<L>* buf1 = buf0 + G * nk;
-		const mpf<L>& rho = *reinterpret_cast<const mpf<L>*>(cx.rho);
-		const mpf<E>& ln2e = *reinterpret_cast<const mpf<E>*>(cx.ln2e);
 		const int prec = cx.prec;
 		const uint32_t n_max = cx.n_max;
 
-		mpf<L> q, qprev, s, a, c4, rp;
+		mpf<L> rho, q, qprev, s, a, ap, c4, rp, tmp;
+		copy(rho, *reinterpret_cast<const mpf<L>*>(cx.rho));
 		const mpf<L>* b0p = nullptr;
 		const mpf<L>* b1p = nullptr;
 		set_zero(s);
 		set_zero(c4);
 		set_zero(rp);
+		set_zero(q);
+		set_zero(qprev);
 		if (active)
 		{
 			// q_k = Delta - k by k rounded decrements                      (real_function.hpp:239 `pow_ -= 1`)
@@ -121,9 +133,11 @@ namespace qb
 			b0p = b + size_t(tr.job0) * (n_max + 1);
 			b1p = tr.job1 >= 0 ? b + size_t(tr.job1) * (n_max + 1) : nullptr;
 			if (k == 0)
-				pow_from_log<L>(c4, *reinterpret_cast<const mpf<E>*>(cx.ln4e), delta[t], ln2e, prec);  // 4^Delta
+				pow_from_log<L>(c4, *reinterpret_cast<const mpf<E>*>(cx.ln4e), q, *reinterpret_cast<const mpf<E>*>(cx.ln2e),
+				                prec);  // 4^Delta
 			else
-				pow_from_log<L>(rp, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe), q, ln2e, prec);       // rho^(q_k)
+				pow_from_log<L>(rp, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe), q, *reinterpret_cast<const mpf<E>*>(cx.ln2e),
+				                prec);  // rho^(q_k)
 		}
 		const int steps = int(n_max) + nk;
 		for (int tau = 0; tau < steps; ++tau)
@@ -136,17 +150,20 @@ namespace qb
 				uint32_t n = n_max - uint32_t(idx);
 				if (k == 0)
 				{
+					copy(ap, b0p[n]);
 					if (b1p)
 					{
-						add(a, b0p[n], b1p[n], prec);
-						mul_2si(a, a, -1);
+						copy(tmp, b1p[n]);
+						add(ap, ap, tmp, prec);
+						mul_2si(ap, ap, -1);
 					}
-					else
-						copy(a, b0p[n]);
-					mul(a, a, c4, prec);                                       // h *= 4^Delta (hor_recursion.cpp:43)
+					mul(a, ap, c4, prec);                                      // h *= 4^Delta (hor_recursion.cpp:43)
 				}
 				else
-					deriv_scale(a, prv[g * nk + k - 1], qprev, n, prec);
+				{
+					copy(ap, prv[g * nk + k - 1]);
+					deriv_scale(a, ap, qprev, n, prec);
+				}
 				if (idx == 0)
 					copy(s, a);
 				else
@@ -157,9 +174,13 @@ namespace qb
 		}
 		if (active)
 		{
-			if (k == 0) pow_from_log<L>(rp, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe), q, ln2e, prec);
-			const mpf<L>* kf = reinterpret_cast<const mpf<L>*>(cx.kfact);
-			deriv_finish(fr[size_t(t) * nk + k], s, rp, kf[k], uint32_t(k), prec);
+			if (k == 0)
+				pow_from_log<L>(rp, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe), q, *reinterpret_cast<const mpf<E>*>(cx.ln2e),
+				                prec);
+			mpf<L> kf, f;
+			copy(kf, reinterpret_cast<const mpf<L>*>(cx.kfact)[k]);
+			deriv_finish(f, s, rp, kf, uint32_t(k), prec);
+			copy(fr[size_t(t) * nk + k], f);
 		}
 	}
 
@@ -173,7 +194,12 @@ namespace qb
 		const int lambda = int(cx.lambda), nk = lambda + 1, dimM = cf_dim(lambda);
 		mpf<L>* f = g + size_t(t) * dimM;
 		const mpf<L>* M = reinterpret_cast<const mpf<L>*>(cx.mat);
-		for (int i = 0; i <= lambda; ++i) rho_to_z_entry(f[i], fr + size_t(t) * nk, 1, M, lambda, i, cx.prec);
+		mpf<L> z;
+		for (int i = 0; i <= lambda; ++i)
+		{
+			rho_to_z_entry(z, fr + size_t(t) * nk, 1, M, lambda, i, cx.prec);
+			copy(f[i], z);
+		}
 		expand_off_diag(f, 1, lambda, delta[t], spin[t], S[t], P[t], cx.eps, cx.prec);
 	}
 
@@ -190,7 +216,7 @@ namespace qb
 		v_to_d_table(v + size_t(i) * cf_dim(int(cx.lambda)), 1, int(cx.lambda), d[i], p4, cx.prec);
 	}
 
-	// term = (table index, d index, sym); output packed per term at out[term * dim_sym_max ...]
+	// term = (table index, d index, sym); output packed per term at out[out_ofs ...]
 	struct TermRef
 	{
 		int32_t table, dix, sym, out_ofs;
@@ -215,7 +241,57 @@ namespace qb
 			rem -= row;
 		}
 		int M = 2 * rem + tr.sym;
-		fblock_entry(out[size_t(tr.out_ofs) + e], v + size_t(tr.dix) * dimM, 1, g + size_t(tr.table) * dimM, 1, lambda, M, N,
-		             cx.prec);
+		mpf<L> r;
+		fblock_entry(r, v + size_t(tr.dix) * dimM, 1, g + size_t(tr.table) * dimM, 1, lambda, M, N, cx.prec);
+		copy(out[size_t(tr.out_ofs) + e], r);
+	}
+
+	// Elementwise primitive (diagnostic entry qb_op_batch): lets the GPU test-suite pin the device build of every
+	// arithmetic routine against MPFR.  op codes follow oracle/ref_capi.cpp.
+	template <int L>
+	__global__ void k_ops(DevCtx cx, int op, int n, const mpf<L>* __restrict__ a, const mpf<L>* __restrict__ b,
+	                      const mpf<L>* __restrict__ c, const int64_t* __restrict__ ia, const int64_t* __restrict__ ib,
+	                      mpf<L>* __restrict__ out)
+	{
+		int i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i >= n) return;
+		constexpr int E = L + QB_EXT_LIMBS;
+		const int prec = cx.prec;
+		mpf<L> x, y, z, r;
+		set_zero(x);
+		set_zero(y);
+		set_zero(z);
+		set_zero(r);
+		if (a) copy(x, a[i]);
+		if (b) copy(y, b[i]);
+		if (c) copy(z, c[i]);
+		int64_t p = ia ? ia[i] : 0, q = ib ? ib[i] : 1;
+		switch (op)
+		{
+		case 0: add(r, x, y, prec); break;
+		case 1: sub(r, x, y, prec); break;
+		case 2: mul(r, x, y, prec); break;
+		case 3: div(r, x, y, prec); break;
+		case 4: fma(r, x, y, z, prec); break;
+		case 6: mul_si(r, x, p, prec); break;
+		case 7: add_si(r, x, p, prec); break;
+		case 8: div_si(r, x, p, prec); break;
+		case 9: mul_q(r, x, p, uint32_t(q), prec); break;
+		case 10: div_q(r, x, p, uint32_t(q), prec); break;
+		case 11: add_q(r, x, p, uint32_t(q), prec); break;
+		case 12: set_q(r, p, uint32_t(q), prec); break;
+		case 13:  // rho^y
+			pow_from_log<L>(r, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe), y, *reinterpret_cast<const mpf<E>*>(cx.ln2e), prec);
+			break;
+		case 14:  // 4^x
+			pow_from_log<L>(r, *reinterpret_cast<const mpf<E>*>(cx.ln4e), x, *reinterpret_cast<const mpf<E>*>(cx.ln2e), prec);
+			break;
+		case 18: si_sub(r, p, x, prec); break;
+		case 20: sub_q(r, x, p, uint32_t(q), prec); break;
+		case 23: r.sk = uint32_t(cmp(x, y) + 1); break;
+		case 24: r.sk = is_integer(x) ? 1u : 0u; break;
+		default: set_nan(r); break;
+		}
+		copy(out[i], r);
 	}
 }  // namespace qb

@@ -16,8 +16,13 @@
 #if defined(__CUDACC__)
 #define QB_HD __host__ __device__
 #define QB_INLINE __forceinline__
-#define QB_NOINLINE __noinline__
+// Device code is fully inlined into the kernels: out-of-line device calls made under warp divergence mis-executed on
+// sm_100a (ptxas 12.9 passes warp-uniform pointer arguments in uniform registers that a diverged sibling path's callee
+// clobbers).  Loops over limbs are kept rolled (QB_ROLL) except the inner product loop, to bound code size.
+#define QB_NOINLINE __forceinline__
+#define QB_ROLL _Pragma("unroll 1")
 #else
+#define QB_ROLL
 #define QB_HD
 #define QB_INLINE inline
 #define QB_NOINLINE
@@ -150,6 +155,7 @@ namespace qb
 		int base = t - (L - 1);
 		uint32_t below = 0u;  // bits below the kept L limbs, collapsed
 		uint32_t guard;       // the limb immediately below the kept ones, after shift
+		QB_ROLL
 		for (int j = 0; j < L; ++j)
 		{
 			int i = base + j;
@@ -165,6 +171,7 @@ namespace qb
 			// everything below `guard`
 			if (i - 1 >= 0 && s && (X[i - 1] << s) != 0u) below = 1u;
 			if (i - 1 >= 0 && !s) below |= (X[i - 1] != 0u);  // when s == 0, X[i-1] is entirely below guard
+			QB_ROLL
 			for (int k = i - 2; k >= 0; --k) below |= (X[k] != 0u);
 		}
 		uint32_t st = (sticky != 0u) | (below != 0u);
@@ -191,6 +198,7 @@ namespace qb
 		if (rnd && (st || lsb))
 		{
 			uint32_t c = ulp;
+			QB_ROLL
 			for (int j = 0; j < L; ++j)
 			{
 				uint32_t v = r.m[j] + c;
@@ -285,6 +293,7 @@ namespace qb
 			swap = true;
 		else if (ea == eb)
 		{
+			QB_ROLL
 			for (int i = N - 1; i >= 0; --i)
 				if (A[i] != B[i])
 				{
@@ -306,11 +315,13 @@ namespace qb
 			// Y lies entirely below the window
 			stk = 1u;
 			OUT[0] = 0u;
+			QB_ROLL
 			for (int i = 0; i < N; ++i) OUT[i + 1] = X[i];
 			if (subtract)
 			{
 				// X - tiny: borrow one unit of the extra limb, remainder becomes positive sticky
 				uint32_t bw = 1u;
+				QB_ROLL
 				for (int i = 0; i < N + 1; ++i)
 				{
 					uint32_t v = OUT[i] - bw;
@@ -327,6 +338,7 @@ namespace qb
 		// Ysh[k] for k in [0, N]: bits of (0:Y[N-1..0]:0_extra) >> d.  Source limb index in the (N+1)-limb frame:
 		// frame[k] = (k >= 1) ? Y[k-1] : 0
 		uint32_t carry = 0u;  // carry / borrow
+		QB_ROLL
 		for (int k = 0; k < N + 1; ++k)
 		{
 			int lo_i = k + q;      // frame index of low part
@@ -357,6 +369,7 @@ namespace qb
 		// bits of Y shifted out below the window
 		{
 			// frame indices [0, q) entirely (frame[0] = 0 contributes nothing) and the low s bits of frame[q]
+			QB_ROLL
 			for (int i = 1; i < q && i <= N; ++i) stk |= (Y[i - 1] != 0u);
 			if (q >= 1 && q <= N && s) stk |= ((Y[q - 1] << (32 - s)) != 0u);
 			if (q >= 1 && q <= N && !s) stk |= 0u;  // frame[q] itself is kept when s == 0
@@ -368,6 +381,7 @@ namespace qb
 			{
 				// shift right by one bit, keep the lost bit in sticky
 				stk |= (OUT[0] & 1u);
+				QB_ROLL
 				for (int k = 0; k < N; ++k) OUT[k] = (OUT[k] >> 1) | (OUT[k + 1] << 31);
 				OUT[N] = (OUT[N] >> 1) | 0x80000000u;
 				oe = ex + 1;
@@ -380,6 +394,7 @@ namespace qb
 			if (stk)
 			{
 				uint32_t bw = 1u;
+				QB_ROLL
 				for (int k = 0; k < N + 1; ++k)
 				{
 					uint32_t v = OUT[k] - bw;
@@ -390,6 +405,7 @@ namespace qb
 			else
 			{
 				bool nz = false;
+				QB_ROLL
 				for (int k = 0; k < N + 1; ++k) nz |= (OUT[k] != 0u);
 				if (!nz)
 				{
@@ -495,10 +511,12 @@ namespace qb
 		if ((P[2 * L - 1] & 0x80000000u) == 0u)
 		{
 			// normalise (exact: the product has at most 64L - 1 significant bits here)
+			QB_ROLL
 			for (int i = 2 * L - 1; i > 0; --i) P[i] = (P[i] << 1) | (P[i - 1] >> 31);
 			P[0] <<= 1;
 			pe -= 1;
 		}
+		QB_ROLL
 		for (int i = 0; i < L; ++i)
 		{
 			C[i] = 0u;
@@ -565,6 +583,7 @@ namespace qb
 		if (uhi == 0u)
 		{
 			uint64_t c = 0;
+			QB_ROLL
 			for (int i = 0; i < L; ++i)
 			{
 				c += uint64_t(a.m[i]) * ulo;
@@ -578,6 +597,7 @@ namespace qb
 		{
 			uint32_t b2[2] = {ulo, uhi};
 			uint32_t am[L];
+			QB_ROLL
 			for (int i = 0; i < L; ++i) am[i] = a.m[i];
 			mul_limbs<L, 2>(X, am, b2);
 		}
@@ -633,6 +653,7 @@ namespace qb
 	QB_HD QB_INLINE uint32_t divrem_1(uint32_t* Q, const uint32_t* X, uint32_t d)
 	{
 		uint64_t rem = 0;
+		QB_ROLL
 		for (int i = N - 1; i >= 0; --i)
 		{
 			uint64_t cur = (rem << 32) | X[i];
@@ -673,6 +694,7 @@ namespace qb
 		// numerator: a.m followed by two zero limbs below  ->  quotient keeps >= 32L + 32 significant bits
 		uint32_t X[L + 2], Q[L + 2];
 		X[0] = X[1] = 0u;
+		QB_ROLL
 		for (int i = 0; i < L; ++i) X[i + 2] = a.m[i];
 		uint32_t rem = divrem_1<L + 2>(Q, X, uint32_t(u));
 		round_to<L, L + 2>(r, sgn, a.exp, Q, rem != 0u, prec);
@@ -691,6 +713,7 @@ namespace qb
 		uint32_t sgn = num < 0 ? SIGN_BIT : 0u;
 		uint64_t u = num < 0 ? uint64_t(0) - uint64_t(num) : uint64_t(num);
 		uint32_t X[L + 4], Q[L + 4];
+		QB_ROLL
 		for (int i = 0; i < L + 2; ++i) X[i] = 0u;
 		X[L + 2] = uint32_t(u);
 		X[L + 3] = uint32_t(u >> 32);
@@ -720,6 +743,7 @@ namespace qb
 		uint32_t X[L + 4], Q[L + 4];
 		uint32_t b2[2] = {uint32_t(u), uint32_t(u >> 32)};
 		uint32_t am[L];
+		QB_ROLL
 		for (int i = 0; i < L; ++i) am[i] = a.m[i];
 		X[0] = X[1] = 0u;
 		mul_limbs<L, 2>(X + 2, am, b2);
@@ -757,6 +781,7 @@ namespace qb
 		uint32_t X[L + 3], Q[L + 3];
 		X[0] = X[1] = 0u;
 		uint64_t c = 0;
+		QB_ROLL
 		for (int i = 0; i < L; ++i)
 		{
 			c += uint64_t(a.m[i]) * den;
@@ -795,6 +820,7 @@ namespace qb
 		{
 			uint32_t T[L + 1];
 			uint64_t c = 0;
+			QB_ROLL
 			for (int i = 0; i < L; ++i)
 			{
 				c += uint64_t(a.m[i]) * den;
@@ -805,6 +831,7 @@ namespace qb
 			// a.m normalised and den >= 1: top nonzero limb is T[L] or T[L-1]
 			int t = T[L] ? L : L - 1;
 			int s = clz32(T[t]);
+			QB_ROLL
 			for (int i = 0; i < N; ++i)
 			{
 				int src = t - (N - 1) + i;
@@ -821,6 +848,7 @@ namespace qb
 		uint64_t u = num < 0 ? uint64_t(0) - uint64_t(num) : uint64_t(num);
 		int nb = 64 - clz64(u);
 		uint64_t un = u << (64 - nb);
+		QB_ROLL
 		for (int i = 0; i < N; ++i) B[i] = 0u;
 		B[N - 1] = uint32_t(un >> 32);
 		B[N - 2] = uint32_t(un);
@@ -833,6 +861,7 @@ namespace qb
 			return;
 		}
 		X[0] = X[1] = 0u;
+		QB_ROLL
 		for (int i = 0; i < N + 1; ++i) X[i + 2] = OUT[i];
 		uint32_t rem = divrem_1<N + 3>(Q, X, den);
 		round_to<L, N + 3>(r, osgn, oe, Q, (rem != 0u) | ostk, prec);
@@ -874,9 +903,11 @@ namespace qb
 		}
 		// numerator window R[0 .. L] (L+1 limbs, R[L] is the overflow limb); divisor D normalised (top bit set)
 		uint32_t R[L + 1], D[L], Q[L + 1];
+		QB_ROLL
 		for (int i = 0; i < L; ++i) D[i] = b.m[i];
 		// ensure numerator < divisor so that every quotient digit fits a limb: if a.m >= b.m use a.m / 2
 		bool ge = true;
+		QB_ROLL
 		for (int i = L - 1; i >= 0; --i)
 			if (a.m[i] != b.m[i])
 			{
@@ -887,19 +918,23 @@ namespace qb
 		uint32_t nextlimb = 0u;  // limb fed in below the window at the first step
 		if (ge)
 		{
+			QB_ROLL
 			for (int i = 0; i < L - 1; ++i) R[i] = (a.m[i] >> 1) | (a.m[i + 1] << 31);
 			R[L - 1] = a.m[L - 1] >> 1;
 			nextlimb = a.m[0] << 31;
 			e += 1;
 		}
 		else
+			QB_ROLL
 			for (int i = 0; i < L; ++i) R[i] = a.m[i];
 		R[L] = 0u;
 		const uint32_t d1 = D[L - 1];
 		const uint32_t d0 = (L >= 2) ? D[L - 2] : 0u;
+		QB_ROLL
 		for (int j = L; j >= 0; --j)
 		{
 			// shift window up by one limb, bringing in the next numerator limb
+			QB_ROLL
 			for (int i = L; i > 0; --i) R[i] = R[i - 1];
 			R[0] = nextlimb;
 			nextlimb = 0u;
@@ -924,6 +959,7 @@ namespace qb
 			}
 			// multiply and subtract
 			uint64_t borrow = 0, carry = 0;
+			QB_ROLL
 			for (int i = 0; i < L; ++i)
 			{
 				carry += qhat * D[i];
@@ -944,6 +980,7 @@ namespace qb
 				// add back
 				qhat -= 1;
 				uint64_t c = 0;
+				QB_ROLL
 				for (int i = 0; i < L; ++i)
 				{
 					c += uint64_t(R[i]) + D[i];
@@ -955,6 +992,7 @@ namespace qb
 			Q[j] = uint32_t(qhat);
 		}
 		uint32_t st = 0u;
+		QB_ROLL
 		for (int i = 0; i <= L; ++i) st |= R[i];
 		round_to<L, L + 1>(r, sgn, e, Q, st != 0u, prec);
 	}
@@ -972,6 +1010,7 @@ namespace qb
 		if (a.exp != b.exp)
 			m = a.exp < b.exp ? -1 : 1;
 		else
+			QB_ROLL
 			for (int i = L - 1; i >= 0; --i)
 				if (a.m[i] != b.m[i])
 				{
@@ -991,6 +1030,7 @@ namespace qb
 		int64_t frac_bits = int64_t(32) * L - a.exp;  // number of low bits that are fractional
 		if (frac_bits <= 0) return true;
 		int q = int(frac_bits >> 5), s = int(frac_bits & 31);
+		QB_ROLL
 		for (int i = 0; i < q && i < L; ++i)
 			if (a.m[i]) return false;
 		if (q < L && s && (a.m[q] & ((1u << s) - 1u))) return false;

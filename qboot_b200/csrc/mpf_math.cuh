@@ -102,14 +102,18 @@ namespace qb
 
 	// r = RN_prec(exp(y * lnx)),  lnx and ln2 given in E = L + QB_EXT_LIMBS limbs
 	template <int L>
+	// r, y thread-local; lnx, ln2 anywhere
 	QB_HD QB_NOINLINE void pow_from_log(mpf<L>& r, const mpf<L + QB_EXT_LIMBS>& lnx, const mpf<L>& y,
 	                        const mpf<L + QB_EXT_LIMBS>& ln2, int prec)
 	{
 		constexpr int E = L + QB_EXT_LIMBS;
-		mpf<E> ye, t, v;
+		// lnx / ln2 may live in global memory: stage them into thread-local records (staging rule, hor.cuh)
+		mpf<E> ye, t, v, lx, l2;
+		copy(lx, lnx);
+		copy(l2, ln2);
 		widen(ye, y);
-		mul(t, ye, lnx, 32 * E);
-		exp_ext(v, t, ln2);
+		mul(t, ye, lx, 32 * E);
+		exp_ext(v, t, l2);
 		narrow(r, v, prec);
 	}
 

@@ -1,0 +1,176 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against golden vectors generated from the
+unmodified reference and against the reference itself (oracle/_ref, shipped as a prebuilt .so) on seeded inputs.
+
+Bar: bit-exact.  Every operation of the engine is the reference's operation (exact result rounded once to nearest-even
+at `prec` bits, in the reference's order), so tables must equal the MPFR build's tables word for word -- far inside the
+north-star tolerance of 2^-(prec-32) relative.
+"""
+import random
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import qboot_b200 as qb
+from tests.util import GOLDEN_OPS, OPS, golden, op_kwargs, same_records
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(prec, n_max, lam, dim="3"):
+    return qb.Engine(prec).context(n_max, lam, dim)
+
+
+@pytest.mark.parametrize("prec", [600, 1024])
+def test_device_primitives_vs_golden(prec):
+    g = golden(f"ops_p{prec}")
+    eng = _engine(prec, 20, 5)
+    for name, keys in GOLDEN_OPS:
+        got = eng.op(OPS[name], **op_kwargs(g, keys))
+        assert same_records(g["r_" + name], got), name
+    n = len(g["ys"])
+    assert np.array_equal(eng.op(OPS["pow"], b=g["ys"]), g["r_pow_rho"])
+    assert np.array_equal(eng.op(OPS["ui_pow"], a=g["ys"]), g["r_pow_4"])
+    assert n > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", [512, 800, 1200, 1536])
+def test_device_primitives_vs_mpfr_live(ref, prec):
+    from tests.golden.make_golden import rnd_num
+
+    rng = random.Random(prec)
+    n = 200
+    a = np.stack([rnd_num(rng, prec) for _ in range(n)])
+    b = np.stack([rnd_num(rng, prec) for _ in range(n)])
+    c = np.stack([rnd_num(rng, prec) for _ in range(n)])
+    for i in range(0, n, 3):
+        b[i] = a[i]
+        b[i, 2] ^= (rng.getrandbits(8) << ((-prec) % 32)) & 0xFFFFFFFF
+        if a[i, 0] & 3:
+            b[i, 0] ^= 0x80000000
+    ia = np.array([rng.choice([0, 1, -1, 2, -3, 7, 400, -12345, 2**31 - 1, 2**40 + 3]) for _ in range(n)], dtype=np.int64)
+    ib = np.array([rng.choice([1, 2, 3, 7, 10, 20, 1000, 2**32 - 1]) for _ in range(n)], dtype=np.int64)
+    ia32 = np.clip(ia, -(2**32 - 1), 2**32 - 1)
+    eng = _engine(prec, 20, 5)
+    for name, kw in [("add", dict(a=a, b=b)), ("sub", dict(a=a, b=b)), ("mul", dict(a=a, b=b)), ("div", dict(a=a, b=b)),
+                     ("fma", dict(a=a, b=b, c=c)), ("mul_si", dict(a=a, ia=ia)), ("add_si", dict(a=a, ia=ia)),
+                     ("div_si", dict(a=a, ia=ia32)), ("si_sub", dict(a=a, ia=ia)), ("mul_q", dict(a=a, ia=ia, ib=ib)),
+                     ("div_q", dict(a=a, ia=ia32, ib=ib)), ("add_q", dict(a=a, ia=ia, ib=ib)), ("set_q", dict(ia=ia, ib=ib))]:
+        assert same_records(ref.op(name, prec, **kw), eng.op(OPS[name], **kw)), name
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["tables_small", "tables_c1", "tables_fracdim", "tables_c3"])
+def test_tables_vs_golden(name):
+    """gBlock tables incl. the unit operator and the divergent stress tensor, Context constants and F/H blocks"""
+    g = golden(name)
+    prec, n_max, lam, dim = int(g["prec"]), int(g["n_max"]), int(g["lam"]), str(g["dim"])
+    eng = _engine(prec, n_max, lam, dim)
+    rho, mat = eng.context_consts()
+    assert np.array_equal(rho, g["rho"]) and np.array_equal(mat, g["mat"])
+    got = eng.gblock(g["spin"], g["delta"], g["S"], g["P"])
+    assert np.array_equal(got, g["g"])
+    n = len(g["spin"])
+    for sym in (0, 1):
+        fb = eng.fblock(list(range(n)), g["fb_d"][sym:sym + 1], [0] * n, [sym] * n)
+        assert np.array_equal(np.stack(fb), g[f"fb_sym{sym}"]), sym
+    eng.close()
+
+
+def _random_inputs(rng, prec, n, spins=(0, 1, 2, 3, 4, 8, 17, 30, 51)):
+    spin = np.array([rng.choice(spins) for _ in range(n)], dtype=np.uint32)
+    delta = np.stack([qb.from_str(repr(rng.uniform(0.55, 60.0)), prec) for _ in range(n)])
+    zero = qb.from_fraction(0, prec)
+    S = np.stack([qb.from_str(repr(rng.uniform(-0.9, 0.9)), prec) if i % 3 else zero for i in range(n)])
+    P = np.stack([qb.from_str(repr(rng.uniform(-0.9, 0.9)), prec) if i % 3 else zero for i in range(n)])
+    return spin, delta, S, P
+
+
+@pytest.mark.parametrize("prec,n_max,lam,dim,n", [(600, 100, 11, "3", 48), (800, 200, 13, "3", 32), (1024, 400, 19, "3", 24),
+                                                  (1536, 800, 27, "3", 6), (1000, 150, 14, "4", 16), (600, 60, 8, "5/2", 16),
+                                                  (1200, 100, 10, "3", 8)])
+def test_tables_vs_reference_live(ref, prec, n_max, lam, dim, n):
+    """BASELINE configs C1-C4 (and other dims / precisions) on seeded inputs, against the reference run on this box"""
+    rng = random.Random(prec * 31 + lam)
+    spin, delta, S, P = _random_inputs(rng, prec, n)
+    eng = _engine(prec, n_max, lam, dim)
+    got = eng.gblock(spin, delta, S, P)
+    want = ref.gblock(prec, n_max, lam, dim, delta, spin, S, P)
+    bad = [i for i in range(n) if not np.array_equal(got[i], want[i])]
+    assert not bad, bad
+    # F / H blocks over the resident tables
+    d = np.stack([qb.from_str("0.5181489", prec), qb.from_str("0.96543695", prec), qb.from_str("1.412625", prec)])
+    tix = [rng.randrange(n) for _ in range(12)]
+    dix = [rng.randrange(3) for _ in range(12)]
+    sym = [rng.randrange(2) for _ in range(12)]
+    fb = eng.fblock(tix, d, dix, sym)
+    for j in range(12):
+        w = ref.fblock(prec, n_max, lam, dim, d[dix[j]], delta[tix[j]], int(spin[tix[j]]), S[tix[j]], P[tix[j]], sym[j])
+        assert np.array_equal(fb[j], w), j
+    eng.close()
+
+
+def test_special_operators_vs_reference(ref):
+    """unit operator, operators at the three families of divergent points, and their neighbours"""
+    prec, n_max, lam, dim = 1024, 120, 9, "3"
+    eng = _engine(prec, n_max, lam, dim)
+    cases = [(0, "0"), (2, "3"), (0, "1/2"), (0, "1"), (1, "2"), (3, "4"), (4, "5"), (0, "0.25"), (2, "3.0000001"),
+             (1, "1"), (5, "6"), (0, "3/2")]
+    spin = np.array([c[0] for c in cases], dtype=np.uint32)
+    delta = np.stack([qb.from_str(c[1], prec) for c in cases])
+    Z = qb.zeros(len(cases), prec)
+    got = eng.gblock(spin, delta, Z, Z)
+    want = ref.gblock(prec, n_max, lam, dim, delta, spin, Z, Z)
+    bad = [cases[i] for i in range(len(cases)) if not same_records(want[i], got[i])]
+    assert not bad, bad
+    eng.close()
+
+
+def test_full_size_properties():
+    """north-star size (lambda = 19, n_Max = 400, 1024-bit): size-independent properties of a PMP-sized batch"""
+    prec, n_max, lam = 1024, 400, 19
+    eng = _engine(prec, n_max, lam)
+    rng = random.Random(5)
+    n = 300
+    spin, delta, S, P = _random_inputs(rng, prec, n, spins=tuple(range(0, 51)))
+    delta[7] = qb.from_fraction(0, prec)  # unit operator
+    spin[7] = 0
+    S[7] = P[7] = 0
+    g1 = eng.gblock(spin, delta, S, P)
+    # (1) results do not depend on batch composition or position (the reference's thread-count independence)
+    perm = np.array(rng.sample(range(n), n))
+    g2 = eng.gblock(spin[perm], delta[perm], S[perm], P[perm])
+    assert np.array_equal(g2, g1[perm])
+    sub = list(range(0, n, 17))
+    g3 = eng.gblock(spin[sub], delta[sub], S[sub], P[sub])
+    assert np.array_equal(g3, g1[sub])
+    # (2) idempotence
+    assert np.array_equal(eng.gblock(spin, delta, S, P), g1)
+    # (3) unit operator: g = (4 rho)^0 * b0 = 1 on the diagonal, derivatives vanish (src/hor_recursion.cpp:20)
+    one = qb.from_fraction(1, prec)
+    assert np.array_equal(g1[7, 0], one)
+    assert all((int(w[0]) & 3) == 0 for w in g1[7, 1:])
+    # (4) every record is canonical: regular numbers are normalised and rounded to prec bits
+    top = g1[..., -1]
+    kind = g1[..., 0] & 3
+    assert np.all((kind == 0) | ((kind == 1) & ((top >> 31) == 1)))
+    # (5) F = 2 proj_odd(v^d g) is linear in g only through exact doubling: F(d, g) computed twice is identical and the
+    #     Even / Odd blocks together hold dim_M entries
+    d = qb.from_str("0.5181489", prec).reshape(1, -1)
+    fo = eng.fblock([3, 3], d, [0, 0], [1, 0])
+    assert len(fo[0]) + len(fo[1]) == eng.dim_M
+    eng.close()
+
+
+def test_error_behaviour():
+    eng = qb.Engine(1024)
+    with pytest.raises(qb.QbError):
+        eng.lib.qb_gblock_run(eng.h) and None
+        eng._check(eng.lib.qb_gblock_run(eng.h), "run")  # no context yet
+    assert eng.lib.qb_gblock_run(eng.h) == -3
+    eng.context(50, 5)
+    assert eng.gblock([], np.zeros((0, eng.W), np.uint32), np.zeros((0, eng.W), np.uint32), np.zeros((0, eng.W), np.uint32)).shape[0] == 0
+    with pytest.raises(qb.QbError):
+        qb.Engine(4096)  # no kernels for this precision
+    eng.close()

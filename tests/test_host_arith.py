@@ -1,0 +1,146 @@
+"""Host build of the engine's __host__ __device__ arithmetic and per-table stages (tests/hostemu) against golden vectors
+from the reference and against the reference live.  This is the CPU-side guard for the CUDA code: same source, host
+compiler.  (The product itself has no CPU path; these entry points exist only in the test harness.)"""
+import ctypes as C
+import random
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from tests.util import GOLDEN_OPS, P, emu_op, golden, op_kwargs, same_records, words
+
+
+def _ext_consts(ref, prec, rho):
+    """[ln2, ln4, ln rho] at L + 3 limbs from MPFR (harness-side constants for pow)"""
+    E = ref.nlimbs(prec) + 3
+    pe = 32 * E
+    ln2 = ref.op("log", pe, a=ref.from_int_exp(0, 2, 0, pe))[0]
+    ln4 = ref.op("log", pe, a=ref.from_int_exp(0, 4, 0, pe))[0]
+    fr = ref.to_fraction(rho, prec)
+    rho_w = ref.from_int_exp(0, fr.numerator, -(fr.denominator.bit_length() - 1), pe)
+    return np.concatenate([ln2, ln4, ref.op("log", pe, a=rho_w)[0]])
+
+
+@pytest.mark.parametrize("prec", [600, 1024])
+def test_primitives_vs_golden(hostemu, prec):
+    g = golden(f"ops_p{prec}")
+    for name, keys in GOLDEN_OPS:
+        kw = op_kwargs(g, keys)
+        assert same_records(g["r_" + name], emu_op(hostemu, name, prec, **kw)), name
+    pos = g["a"].copy()
+    pos[:, 0] &= 0x7FFFFFFF
+    out = np.zeros_like(pos)
+    hostemu.qbh_sqrt(prec, len(pos), P(pos), P(out))
+    assert same_records(g["r_sqrt"], out)
+
+
+@pytest.mark.parametrize("prec", [64, 65, 100, 128, 150, 256, 512, 800, 1000, 1200, 1536])
+def test_primitives_vs_mpfr_live(hostemu, ref, prec):
+    rng = random.Random(prec)
+    from tests.golden.make_golden import rnd_num
+
+    n = 120
+    a = np.stack([rnd_num(rng, prec) for _ in range(n)])
+    b = np.stack([rnd_num(rng, prec) for _ in range(n)])
+    c = np.stack([rnd_num(rng, prec) for _ in range(n)])
+    for i in range(0, n, 3):
+        b[i] = a[i]
+        b[i, 2] ^= (rng.getrandbits(8) << ((-prec) % 32)) & 0xFFFFFFFF
+        if a[i, 0] & 3:
+            b[i, 0] ^= 0x80000000
+    ia = np.array([rng.choice([0, 1, -1, 2, -3, 7, 400, -12345, 2**31 - 1, 2**40 + 3, rng.randint(-10**6, 10**6)]) for _ in range(n)], dtype=np.int64)
+    ib = np.array([rng.choice([1, 2, 3, 7, 10, 20, 1000, 2**32 - 1, rng.randint(1, 10**6)]) for _ in range(n)], dtype=np.int64)
+    ia32 = np.clip(ia, -(2**32 - 1), 2**32 - 1)
+    prod = ref.op("mul", prec, a=a, b=b)
+    prod[:, 0] ^= 0x80000000
+    cases = [("add", dict(a=a, b=b)), ("sub", dict(a=a, b=b)), ("mul", dict(a=a, b=b)), ("div", dict(a=a, b=b)),
+             ("fma", dict(a=a, b=b, c=c)), ("fma", dict(a=a, b=b, c=prod)), ("mul_si", dict(a=a, ia=ia)),
+             ("add_si", dict(a=a, ia=ia)), ("div_si", dict(a=a, ia=ia32)), ("si_sub", dict(a=a, ia=ia)),
+             ("mul_q", dict(a=a, ia=ia, ib=ib)), ("div_q", dict(a=a, ia=ia32, ib=ib)), ("add_q", dict(a=a, ia=ia, ib=ib)),
+             ("sub_q", dict(a=a, ia=ia, ib=ib)), ("set_q", dict(ia=ia, ib=ib))]
+    for name, kw in cases:
+        assert same_records(ref.op(name, prec, **kw), emu_op(hostemu, name, prec, **kw)), name
+    for name, kw in [("cmp", dict(a=a, b=b)), ("isint", dict(a=a))]:
+        assert np.array_equal(ref.op(name, prec, **kw)[:, 0], emu_op(hostemu, name, prec, **kw)[:, 0]), name
+    pos = a.copy()
+    pos[:, 0] &= 0x7FFFFFFF
+    out = np.zeros_like(pos)
+    hostemu.qbh_sqrt(prec, n, P(pos), P(out))
+    assert same_records(ref.op("sqrt", prec, a=pos), out)
+
+
+@pytest.mark.parametrize("prec", [600, 1024])
+def test_pow_vs_golden(hostemu, ref, prec):
+    g = golden(f"ops_p{prec}")
+    rho = ref.op("si_sub", prec, a=ref.op("sqrt", prec, a=ref.from_int_exp(0, 8, 0, prec)), ia=[3])[0]
+    ce = _ext_consts(ref, prec, rho)
+    E2 = ref.nlimbs(prec) + 3 + 2
+    ln2, ln4, lnrho = ce[:E2], ce[E2:2 * E2], ce[2 * E2:]
+    n = len(g["ys"])
+    got = emu_op(hostemu, "pow", prec, a=np.tile(rho, (n, 1)), b=g["ys"], consts=np.concatenate([ln2, lnrho]))
+    assert np.array_equal(got, g["r_pow_rho"])
+    got = emu_op(hostemu, "ui_pow", prec, a=g["ys"], consts=np.concatenate([ln2, ln4]))
+    assert np.array_equal(got, g["r_pow_4"])
+
+
+@pytest.mark.parametrize("prec,lam", [(600, 11), (1024, 19), (256, 5)])
+def test_context_constants(hostemu, ref, prec, lam):
+    """rho, the rho->z matrix (bit-exact) and the extended logarithms (<= 1 ulp at L + 3 limbs)"""
+    W, E = words(prec), ref.nlimbs(prec) + 3
+    rho, mat = ref.context_consts(prec, 30, lam, "3")
+    r2 = np.zeros(W, dtype=np.uint32)
+    m2 = np.zeros((lam + 1, lam + 1, W), dtype=np.uint32)
+    kf = np.zeros((lam + 1, W), dtype=np.uint32)
+    ext = np.zeros((3, E + 2), dtype=np.uint32)
+    assert hostemu.qbh_context_consts(prec, lam, P(r2), P(m2), P(kf), P(ext)) == 0
+    assert np.array_equal(rho, r2)
+    assert np.array_equal(mat, m2)
+    want = _ext_consts(ref, prec, rho).reshape(3, E + 2)
+    pe = 32 * E
+    for i in range(3):
+        a, b = ref.to_fraction(want[i], pe), ref.to_fraction(ext[i], pe)
+        assert abs(a - b) <= abs(a) * Fraction(2) ** (-pe + 1), i
+
+
+def _run_table(hostemu, ref, g, t, ce):
+    prec, n_max, lam = int(g["prec"]), int(g["n_max"]), int(g["lam"])
+    W = words(prec)
+    eps = Fraction(str(g["dim"])) / 2 - 1
+    dm = (lam + 2) * (lam + 2) // 4
+    out = np.zeros((dm, W), dtype=np.uint32)
+    b0 = g["hblock"][t][0].copy()
+    k = hostemu.qbh_gblock(prec, n_max, lam, C.c_int64(eps.numerator), eps.denominator, P(g["delta"][t].copy()),
+                           int(g["spin"][t]), P(g["S"][t].copy()), P(g["P"][t].copy()), P(b0), P(g["rho"].copy()),
+                           P(np.ascontiguousarray(g["mat"])), P(ce), P(out), None)
+    assert k == dm
+    return out
+
+
+@pytest.mark.parametrize("name", ["tables_small", "tables_c1", "tables_fracdim"])
+def test_table_stages_vs_golden(hostemu, ref, name):
+    g = golden(name)
+    prec, n_max, lam = int(g["prec"]), int(g["n_max"]), int(g["lam"])
+    W = words(prec)
+    eps = Fraction(str(g["dim"])) / 2 - 1
+    ce = _ext_consts(ref, prec, g["rho"])
+    for t in range(len(g["spin"])):
+        spin = int(g["spin"][t])
+        if (int(g["delta"][t][0]) & 3) == 0 or (spin == 2 and t == 1 and str(g["dim"]) == "3"):
+            continue  # unit / divergent operators are planned by the engine's host side (covered by the GPU tests)
+        K, deg = (6, 3) if spin == 0 else (8, 4)
+        rec = np.zeros((K, deg + 1, W), dtype=np.uint32)
+        assert hostemu.qbh_rec_coeffs(prec, C.c_int64(eps.numerator), eps.denominator, P(g["delta"][t].copy()), spin,
+                                      P(g["S"][t].copy()), P(g["P"][t].copy()), P(rec)) == K
+        assert np.array_equal(rec, g["rec"][t, :K, :deg + 1]), ("rec", t)
+        hb = np.zeros((n_max + 1, W), dtype=np.uint32)
+        hostemu.qbh_hblock(prec, n_max, C.c_int64(eps.numerator), eps.denominator, P(g["delta"][t].copy()), spin,
+                           P(g["S"][t].copy()), P(g["P"][t].copy()), P(g["hblock"][t][0].copy()), P(hb))
+        assert np.array_equal(hb, g["hblock"][t]), ("hblock", t)
+        tab = _run_table(hostemu, ref, g, t, ce)
+        assert np.array_equal(tab, g["g"][t]), ("gblock", t)
+        for sym in (0, 1):
+            want = g[f"fb_sym{sym}"][t]
+            fo = np.zeros_like(want)
+            cnt = hostemu.qbh_fblock(prec, lam, P(g["fb_d"][sym].copy()), P(tab), sym, P(ce), P(fo))
+            assert cnt == len(want) and np.array_equal(fo, want), ("fblock", t, sym)
