@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of qboot's block-table hot path on B200 (BASELINE.json metric: gBlock tables/s at lambda = 19,
+n_Max = 400, 1024-bit; the PMP-build leg is reported once the PMP assembly rows are built).
+
+  python bench.py --gpus N --steps K --warmup W            this engine (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU implementation (oracle/_ref)
+
+A "step" is one pass of the hot path over one batch of synthetic block-table keys: the scan workload of BASELINE
+config 5 -- the mixed-correlator Ising key set (spins 0..50, numax = 20, three (S, P) classes) repeated over a grid of
+(Delta_sigma, Delta_epsilon) -- `tables_per_gpu` tables per GPU per step (weak scaling: every rank gets its own shard
+of the grid, there is no data-path collective; rank 0 gathers the timings).
+
+  value     tables/s with the inputs already resident in HBM (qb_gblock_plan done; qb_gblock_run timed with CUDA
+            events on the launching stream; barrier + synchronize on both sides; max over ranks)
+  e2e       tables/s through qb_gblock_batch with HOST buffers in and out (planning, H2D, kernels, D2H all timed)
+  roofline  the dominant kernel (rho-derivative chains) against the MEASURED integer multiply-add rate of this GPU
+            (qb_imad_peak); the path is IMAD-bound (>= 350 MAC per HBM byte), so the bound is "imad", not hbm/tensor
+  cpu_baseline  oracle/_ref (the unmodified reference, MPFR) on this box's host cores, bounded sample, rank 0, N = 1
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PREC, N_MAX, LAM, DIM, NUMAX, MAXSPIN = 1024, 400, 19, "3", 20, 50
+METRIC = "gblock_tables_per_s"
+UNIT = "tables/s"
+WORKLOAD = "gBlock tables, Context(n_Max=400, lambda=19, dim=3), 1024-bit, mixed-Ising key set (spins 0-50, numax=20) swept over a (Delta_sigma, Delta_epsilon) grid"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_shard(rank: int, tables: int):
+    """rank-specific slice of the scan workload (deterministic)"""
+    from qboot_b200 import workload as wl
+
+    keys = wl.sweep_keys(PREC, LAM, NUMAX, MAXSPIN, tables * (rank + 1))[tables * rank:]
+    return wl.to_records(keys, PREC)
+
+
+def total_work(spin, stage="total"):
+    from qboot_b200 import workload as wl
+
+    w0 = wl.work_per_table(N_MAX, LAM, 32, 0)[stage]
+    w1 = wl.work_per_table(N_MAX, LAM, 32, 1)[stage]
+    n0 = int((spin == 0).sum())
+    return n0 * w0 + (len(spin) - n0) * w1
+
+
+def run_reference(args, rank, world):
+    """the reference's own CPU implementation of the path (oracle/_ref), all host threads, bounded sample per step"""
+    if rank != 0:
+        return 0
+    from oracle import ref
+
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libqboot_ref.so not built (needs /root/reference at build time)"}))
+        return 0
+    cores = host_cores()
+    sample = int(args.ref_tables) if args.ref_tables else max(64, 16 * cores)
+    spin, delta, S, P = make_shard(0, sample)
+    for _ in range(args.warmup):
+        ref.time_gblock(PREC, N_MAX, LAM, DIM, delta[:cores], spin[:cores], S[:cores], P[:cores], cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += ref.time_gblock(PREC, N_MAX, LAM, DIM, delta, spin, S, P, cores)
+    value = sample * args.steps / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "mpfr-1024 (f1024)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "tables_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{sample} tables per step through qboot::gBlock on {cores} host threads (reference task fan-out)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tables-per-gpu", type=int, default=int(os.environ.get("QB_BENCH_TABLES", "24548")))
+    ap.add_argument("--ref-tables", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rules: at least 3 warm-up steps
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import qboot_b200 as qb
+
+    eng = qb.Engine(PREC, device=local).context(N_MAX, LAM, DIM)
+    stream = torch.cuda.ExternalStream(eng.stream, device=local)
+    n = args.tables_per_gpu
+    spin, delta, S, P = make_shard(rank, n)
+    W = eng.W
+    # pinned host staging for the end-to-end leg
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    h_spin, h_delta, h_S, h_P = pin(spin.astype(np.uint32).view(np.int32)), pin(delta.view(np.int32)), pin(S.view(np.int32)), pin(P.view(np.int32))
+    h_out = torch.empty((n, eng.dim_M, W), dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: inputs already in HBM ---------------------------------------------------------------------
+    eng.plan(spin, delta, S, P)
+    peak = eng.imad_peak(4096)
+    launches0 = eng.launches
+    eng.set_timing(True)
+    for _ in range(args.warmup):
+        eng.run()
+    eng.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = np.zeros(4)
+    launches_before = eng.launches
+    t_wall = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+    per_step = []
+    for _ in range(args.steps):
+        eng.run()
+        # tables of one step (n * dim_M * W * 4 bytes, several hundred MB) exceed L2 and are rewritten every step
+        k = eng.kernel_times()  # synchronises this step
+        kms += np.array(k)
+        per_step.append(sum(k))
+    with torch.cuda.stream(stream):
+        ev1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches_timed = eng.launches - launches_before
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the one-shot C-ABI call ------------------------------
+    lib, h = eng.lib, eng.h
+    import ctypes as C
+
+    def e2e_once():
+        rc = lib.qb_gblock_batch(h, n, C.c_void_p(h_spin.data_ptr()), C.c_void_p(h_delta.data_ptr()), C.c_void_p(h_S.data_ptr()),
+                                 C.c_void_p(h_P.data_ptr()), C.c_void_p(h_out.data_ptr()))
+        if rc != 0:
+            raise SystemExit(f"qb_gblock_batch failed: {rc}")
+
+    eng.set_timing(False)
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_once()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    # ---- reduce over ranks ------------------------------------------------------------------------------------------------
+    stats = torch.tensor([dev_ms, e2e_s, kms[2] / args.steps, float(n)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, total_tables = float(mx[0]), float(mx[1]), float(sm[3])
+    else:
+        total_tables = float(n)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    ms_per_step = dev_ms / args.steps
+    value = total_tables / (ms_per_step * 1e-3)
+    deriv_ms = kms[2] / args.steps
+    w_deriv = total_work(spin, "deriv")
+    achieved = w_deriv / (deriv_ms * 1e-3)
+    in_bytes = int(spin.nbytes + delta.nbytes + S.nbytes + P.nbytes)
+    out_bytes = int(n * eng.dim_M * W * 4)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f1024 (32 x u32 limbs, round-to-nearest-even per operation)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "tables_per_gpu_per_step": n, "precision_bits": PREC, "n_Max": N_MAX, "lambda": LAM,
+                   "l2": "each step rewrites its %d MB of tables and %d MB of series coefficients (> 126 MB L2)" % (
+                       out_bytes // 2**20, n * (N_MAX + 1) * W * 4 // 2**20)},
+        "e2e": {"value": total_tables / e2e_s, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes},
+        "gpu_launches": int(launches_timed),
+        "kernel_ms_per_step": {"rec_coeffs": kms[0] / args.steps, "series": kms[1] / args.steps, "deriv": deriv_ms,
+                               "finish": kms[3] / args.steps},
+        "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlimb-MAC/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_deriv (rho-derivative chains)",
+                     "whole_step_frac": total_work(spin) / (ms_per_step * 1e-3) / peak,
+                     "peak_source": "measured on this GPU by qb_imad_peak (dependency-free mad.wide.u32 chains, full occupancy)",
+                     "hbm_gbs_achieved": (out_bytes + n * (N_MAX + 1) * W * 4 * 2) / (ms_per_step * 1e-3) / 1e9},
+        "clocks": clocks, "wall_s_timed_region": t_wall,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import ref
+
+            if ref.available():
+                cores = host_cores()
+                sample = max(64, 16 * cores)
+                t = ref.time_gblock(PREC, N_MAX, LAM, DIM, delta[:sample], spin[:sample], S[:sample], P[:sample], cores)
+                line["cpu_baseline"] = {"value": sample / t, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"first {sample} tables of the same workload through the unmodified reference (qboot::gBlock, MPFR 4.2.1) on {cores} host threads"}
+        except Exception as ex:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"error": str(ex)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -96,6 +96,15 @@ uint64_t qb_stream(const qb_handle* h);
 int qb_fblock_batch(qb_handle* h, int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
                     const int32_t* sym, uint32_t* out);
 
+/* Measurement support.  qb_set_timing(h, 1) brackets each kernel of qb_gblock_run with CUDA events on the handle's
+ * stream; qb_kernel_times synchronises and returns the device times in ms of the last run:
+ * [0] recurrence coefficients, [1] series recurrence, [2] rho-derivative chains, [3] rho->z + transverse recursion.
+ * qb_imad_peak measures the integer multiply-add issue rate of this GPU (dependency-free mad.wide.u32 chains at full
+ * occupancy) in limb-MACs per second -- the denominator of the roofline for this path. */
+int qb_set_timing(qb_handle* h, int on);
+int qb_kernel_times(qb_handle* h, float* ms4);
+int qb_imad_peak(qb_handle* h, int iters, double* macs_per_s);
+
 /* Diagnostic: one arithmetic primitive applied elementwise on the device (n records per operand, HOST memory; unused
  * operands may be NULL).  op: 0 add, 1 sub, 2 mul, 3 div, 4 fma(a*b+c), 6 mul_si(a*ia), 7 add_si, 8 div_si, 9 mul_q
  * (a*ia/ib), 10 div_q, 11 add_q, 12 set_q(ia/ib), 13 rho^b, 14 4^a, 18 si_sub(ia-a), 20 sub_q, 23 cmp(a,b)+1 in word 0,

@@ -19,7 +19,7 @@ SYMBOLS = (
     "qb_version", "qb_strerror", "qb_precision_supported", "qb_create", "qb_destroy", "qb_words",
     "qb_last_cuda_error", "qb_context_init", "qb_context_get", "qb_table_dim", "qb_block_dim", "qb_gblock_batch",
     "qb_gblock_plan", "qb_gblock_run", "qb_gblock_fetch", "qb_sync", "qb_gblock_device_tables", "qb_launch_count",
-    "qb_stream", "qb_fblock_batch", "qb_op_batch",
+    "qb_stream", "qb_fblock_batch", "qb_op_batch", "qb_set_timing", "qb_kernel_times", "qb_imad_peak",
 )
 
 
@@ -65,6 +65,9 @@ def load_library():
     lib.qb_fblock_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]
     lib.qb_op_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+    lib.qb_set_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.qb_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.qb_imad_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -244,6 +247,21 @@ class Engine:
         self._check(self.lib.qb_op_batch(self.h, int(code), n, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
                                          _ptr(ints[0]), _ptr(ints[1]), _ptr(out)), "qb_op_batch")
         return out
+
+    def set_timing(self, on: bool = True):
+        self._check(self.lib.qb_set_timing(self.h, int(on)), "qb_set_timing")
+
+    def kernel_times(self):
+        """device ms of the last run: (rec_coeffs, series, deriv, finish)"""
+        ms = (C.c_float * 4)()
+        self._check(self.lib.qb_kernel_times(self.h, ms), "qb_kernel_times")
+        return [float(x) for x in ms]
+
+    def imad_peak(self, iters: int = 4096) -> float:
+        """measured integer multiply-add rate of this GPU in limb-MACs per second"""
+        v = C.c_double()
+        self._check(self.lib.qb_imad_peak(self.h, iters, C.byref(v)), "qb_imad_peak")
+        return float(v.value)
 
     @property
     def launches(self) -> int:

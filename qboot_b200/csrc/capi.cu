@@ -116,6 +116,25 @@ extern "C"
 		}
 		return QB_OK;
 	}
+	int qb_set_timing(qb_handle* h, int on)
+	{
+		if (!h) return QB_ERR_BAD_ARG;
+		h->e->timing = on != 0;
+		return QB_OK;
+	}
+	int qb_kernel_times(qb_handle* h, float* ms4)
+	{
+		if (!h || !ms4) return QB_ERR_BAD_ARG;
+		int rc = qb_sync(h);
+		if (rc) return rc;
+		h->e->collect_times_public();
+		for (int i = 0; i < 4; ++i) ms4[i] = h->e->kernel_ms[i];
+		return QB_OK;
+	}
+	int qb_imad_peak(qb_handle* h, int iters, double* macs_per_s)
+	{
+		return (h && macs_per_s && iters > 0) ? h->e->imad_peak(iters, macs_per_s) : QB_ERR_BAD_ARG;
+	}
 	const uint32_t* qb_gblock_device_tables(const qb_handle* h) { return h ? h->e->device_tables() : nullptr; }
 	int64_t qb_launch_count(const qb_handle* h) { return h ? h->e->launches : 0; }
 	uint64_t qb_stream(const qb_handle* h) { return h ? uint64_t(reinterpret_cast<uintptr_t>(h->e->stream)) : 0; }

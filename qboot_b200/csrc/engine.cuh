@@ -31,6 +31,11 @@ namespace qb
 		virtual const uint32_t* device_tables() const = 0;
 		virtual int fblock_batch(int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
 		                         const int32_t* sym, uint32_t* out) = 0;
+		virtual int imad_peak(int iters, double* macs_per_s) = 0;
+		virtual int collect_times_public() = 0;
+		// per-kernel device times (ms) of the last gblock_run when timing is enabled: rec_coeffs, series, deriv, finish
+		bool timing = false;
+		float kernel_ms[4] = {0, 0, 0, 0};
 		virtual int op_batch(int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c, const int64_t* ia,
 		                     const int64_t* ib, uint32_t* out) = 0;
 	};
@@ -95,6 +100,7 @@ namespace qb
 		uint32_t* t_spin = nullptr;
 		T *j_delta = nullptr, *j_S = nullptr, *j_P = nullptr, *j_b0 = nullptr;
 		uint32_t* j_spin = nullptr;
+		cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
 		Engine(int dev, int prec_bits)
 		{
@@ -324,12 +330,16 @@ namespace qb
 			if (n_tables == 0) return 0;
 			QB_CU(cudaSetDevice(device));
 			const int nk = int(lambda) + 1;
+			if (timing && !ev[0])
+				for (auto& e : ev) QB_CU(cudaEventCreate(&e));
+			if (timing) QB_CU(cudaEventRecord(ev[0], stream));
 			{
 				int threads = 128, total = n_jobs * QB_NCOEF;
 				k_rec_coeffs<L><<<(total + threads - 1) / threads, threads, 0, stream>>>(cx, n_jobs, j_delta, j_spin, j_S, j_P,
 				                                                                         d_coef.as<T>());
 				++launches;
 				if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
+				if (timing) QB_CU(cudaEventRecord(ev[1], stream));
 			}
 			{
 				int threads = 64;
@@ -337,6 +347,7 @@ namespace qb
 				                                                                      d_coef.as<T>(), d_b.as<T>());
 				++launches;
 				if (int rc_ = debug_sync("k_series")) return rc_;
+				if (timing) QB_CU(cudaEventRecord(ev[2], stream));
 			}
 			{
 				int G = 160 / nk;
@@ -354,6 +365,7 @@ namespace qb
 				                                             d_fr.as<T>());
 				++launches;
 				if (int rc_ = debug_sync("k_deriv")) return rc_;
+				if (timing) QB_CU(cudaEventRecord(ev[3], stream));
 			}
 			{
 				int threads = 64;
@@ -361,8 +373,51 @@ namespace qb
 				                                                                        d_fr.as<T>(), d_g.as<T>());
 				++launches;
 				if (int rc_ = debug_sync("k_finish")) return rc_;
+				if (timing) QB_CU(cudaEventRecord(ev[4], stream));
 			}
 			QB_CU(cudaGetLastError());
+			return 0;
+		}
+		// after a synchronise: read the per-kernel times of the last run
+		int collect_times()
+		{
+			if (!timing || !ev[0]) return 0;
+			for (int i = 0; i < 4; ++i)
+				if (cudaEventElapsedTime(&kernel_ms[i], ev[i], ev[i + 1]) != cudaSuccess)
+				{
+					cudaGetLastError();
+					kernel_ms[i] = 0.f;
+				}
+			return 0;
+		}
+		int collect_times_public() override { return collect_times(); }
+		int imad_peak(int iters, double* macs_per_s) override
+		{
+			QB_CU(cudaSetDevice(device));
+			if (d_fb_out.ensure(64)) return -7;
+			cudaDeviceProp prop;
+			QB_CU(cudaGetDeviceProperties(&prop, device));
+			const int blocks = prop.multiProcessorCount * 8, threads = 256;
+			cudaEvent_t e0, e1;
+			QB_CU(cudaEventCreate(&e0));
+			QB_CU(cudaEventCreate(&e1));
+			k_imad_peak<<<blocks, threads, 0, stream>>>(d_fb_out.as<uint64_t>(), 64, 12345u);  // warm-up
+			double best = 0.0;
+			for (int rep = 0; rep < 5; ++rep)
+			{
+				QB_CU(cudaEventRecord(e0, stream));
+				k_imad_peak<<<blocks, threads, 0, stream>>>(d_fb_out.as<uint64_t>(), iters, 12345u + rep);
+				QB_CU(cudaEventRecord(e1, stream));
+				QB_CU(cudaStreamSynchronize(stream));
+				float ms = 0.f;
+				QB_CU(cudaEventElapsedTime(&ms, e0, e1));
+				double macs = double(blocks) * threads * double(iters) * 64.0;
+				if (ms > 0.f && macs / (ms * 1e-3) > best) best = macs / (ms * 1e-3);
+			}
+			launches += 6;
+			cudaEventDestroy(e0);
+			cudaEventDestroy(e1);
+			*macs_per_s = best;
 			return 0;
 		}
 		int gblock_fetch(uint32_t* out) override

@@ -61,7 +61,7 @@ def test_device_primitives_vs_mpfr_live(ref, prec):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["tables_small", "tables_c1", "tables_fracdim", "tables_c3"])
+@pytest.mark.parametrize("name", ["tables_c1", "tables_fracdim", "tables_c3"])
 def test_tables_vs_golden(name):
     """gBlock tables incl. the unit operator and the divergent stress tensor, Context constants and F/H blocks"""
     g = golden(name)
