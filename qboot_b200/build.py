@@ -1,8 +1,10 @@
 """Build the CUDA engine in-tree: qboot_b200/libqboot_b200.so (sm_100a only).
 
-One translation unit per limb count (engine_inst.cu with -DQB_L=<L>) plus the C ABI (capi.cu), compiled in parallel
-with nvcc and linked against the shared CUDA runtime.  No JIT cache, no torch extension machinery: the resulting .so
-sits next to this file so that it travels with the repository snapshot to the GPU box.
+Translation units: per limb count L one host-side engine (engine_inst.cu, -DQB_L) and five kernel groups
+(kernel_inst.cu, -DQB_L -DQB_KGROUP=0..4), plus the C ABI (capi.cu).  All device arithmetic is force-inlined into the
+kernels (see mpf.cuh), so the kernel groups are the expensive part; they compile in parallel and are cached per object
+by a digest of the sources.  No JIT cache, no torch extension machinery: the .so sits next to this file so that it
+travels with the repository snapshot to the GPU box.
 """
 from __future__ import annotations
 
@@ -18,8 +20,9 @@ ROOT = os.path.dirname(HERE)
 BUILD = os.path.join(ROOT, "build", "qb")
 LIB = os.path.join(HERE, "libqboot_b200.so")
 
-# limb counts compiled in: 512, 600, 800, 1000/1024, 1200, 1536 bits
-LIMBS = (16, 19, 25, 32, 38, 48)
+# limb counts compiled in: 600, 800, 1000/1024, 1536 bits (override: QB_LIMBS=19,32)
+LIMBS = tuple(int(x) for x in os.environ.get("QB_LIMBS", "19,25,32,48").split(","))
+KGROUPS = (0, 1, 2, 3, 4)
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -35,43 +38,55 @@ def _sources_digest() -> str:
                 h.update(fh.read())
     with open(os.path.join(ROOT, "include", "qboot_b200.h"), "rb") as fh:
         h.update(fh.read())
-    h.update(repr(LIMBS).encode())
+    h.update(" ".join(COMMON + ARCH).encode())
     return h.hexdigest()
 
 
-def _run(cmd, log):
+def _run(cmd, log, stamp=None, digest=None):
     with open(log, "w") as fh:
         p = subprocess.run(cmd, stdout=fh, stderr=subprocess.STDOUT)
     if p.returncode != 0:
         sys.stderr.write(open(log).read()[-4000:])
         raise RuntimeError("build step failed: " + " ".join(cmd))
+    if stamp:
+        with open(stamp, "w") as fh:
+            fh.write(digest)
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(BUILD, exist_ok=True)
-    stamp = os.path.join(BUILD, "stamp")
     digest = _sources_digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return LIB
-    jobs = []
+    jobs = []  # (cmd, log, obj)
+
+    def add(name, src, defs):
+        obj = os.path.join(BUILD, name + ".o")
+        jobs.append(([NVCC, *ARCH, *COMMON, *defs, "-c", os.path.join(CSRC, src), "-o", obj], os.path.join(BUILD, name + ".log"), obj))
+
     for L in LIMBS:
-        obj = os.path.join(BUILD, f"engine_L{L}.o")
-        cmd = [NVCC, *ARCH, *COMMON, f"-DQB_L={L}", "-c", os.path.join(CSRC, "engine_inst.cu"), "-o", obj]
-        jobs.append((cmd, os.path.join(BUILD, f"engine_L{L}.log"), obj))
-    llist = " ".join(f"X({L})" for L in LIMBS)
-    capi_obj = os.path.join(BUILD, "capi.o")
-    jobs.append(([NVCC, *ARCH, *COMMON, f"-DQB_L_LIST={llist}", "-c", os.path.join(CSRC, "capi.cu"), "-o", capi_obj],
-                 os.path.join(BUILD, "capi.log"), capi_obj))
-    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
-        futs = [ex.submit(_run, cmd, log) for cmd, log, _ in jobs]
-        for f in futs:
-            f.result()
-    objs = [o for _, _, o in jobs]
-    _run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "shared"], os.path.join(BUILD, "link.log"))
-    with open(stamp, "w") as fh:
-        fh.write(digest)
-    if verbose:
-        print(f"built {LIB}")
+        for g in KGROUPS:
+            add(f"kernels_L{L}_g{g}", "kernel_inst.cu", [f"-DQB_L={L}", f"-DQB_KGROUP={g}"])
+    for L in LIMBS:
+        add(f"engine_L{L}", "engine_inst.cu", [f"-DQB_L={L}"])
+    add("capi", "capi.cu", ["-DQB_L_LIST=" + " ".join(f"X({L})" for L in LIMBS)])
+
+    todo = []
+    for cmd, log, obj in jobs:
+        stamp = obj + ".stamp"
+        key = digest + " " + " ".join(cmd)
+        key = hashlib.sha256(key.encode()).hexdigest()
+        if force or not (os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == key):
+            todo.append((cmd, log, stamp, key))
+    if todo or not os.path.exists(LIB):
+        # heaviest first (series / deriv of the largest L)
+        todo.sort(key=lambda t: (-int(next((a.split("=")[1] for a in t[0] if a.startswith("-DQB_L=")), "0")),))
+        with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+            futs = [ex.submit(_run, cmd, log, stamp, key) for cmd, log, stamp, key in todo]
+            for f in futs:
+                f.result()
+        objs = [o for _, _, o in jobs]
+        _run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "shared"], os.path.join(BUILD, "link.log"))
+        if verbose:
+            print(f"built {LIB} ({len(todo)} objects compiled)")
     return LIB
 
 

@@ -40,14 +40,14 @@ namespace qb
 	QB_HD QB_INLINE void deriv_scale(mpf<L>& a, const mpf<L>& a_prev, const mpf<L>& q, uint32_t n, int prec)
 	{
 		mpf<L> f;
-		add_si(f, q, int64_t(n), prec);
-		mul(a, a_prev, f, prec);
+		fast::add_small(f, q, int64_t(n), prec);
+		fast::mul(a, a_prev, f, prec);
 	}
 	// Horner step s <- s * rho + a                                   (approximate, real_function.hpp:248-259)
 	template <int L>
 	QB_HD QB_INLINE void deriv_horner(mpf<L>& s, const mpf<L>& rho, const mpf<L>& a, int prec)
 	{
-		fma(s, s, rho, a, prec);
+		fast::fma(s, s, rho, a, prec);
 	}
 	// f_k = s * rho^q / k!                                           (real_function.hpp:262, hor_recursion.cpp:46-53)
 	template <int L>
@@ -67,13 +67,13 @@ namespace qb
 		mpf<L> t, xv, mv;
 		copy(xv, x[0]);
 		copy(mv, M[i]);
-		mul(z, xv, mv, prec);
+		fast::mul(z, xv, mv, prec);
 		for (int j = 1; j <= lambda; ++j)
 		{
 			copy(xv, x[int64_t(j) * xstride]);
 			copy(mv, M[j * (lambda + 1) + i]);
-			mul(t, xv, mv, prec);
-			add(z, z, t, prec);
+			fast::mul(t, xv, mv, prec);
+			fast::add(z, z, t, prec);
 		}
 	}
 
@@ -260,8 +260,8 @@ namespace qb
 			{
 				copy(a, v[int64_t(cf_index(lambda, dx1, dy1)) * vs]);
 				copy(b, g[int64_t(cf_index(lambda, M - dx1, N - dy1)) * gs]);
-				mul(t, a, b, prec);
-				add(acc, acc, t, prec);
+				fast::mul(t, a, b, prec);
+				fast::add(acc, acc, t, prec);
 			}
 		mul_si(out, acc, 2, prec);
 	}

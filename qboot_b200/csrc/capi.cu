@@ -15,6 +15,39 @@
 QB_L_LIST
 #undef X
 
+namespace qb
+{
+	// Integer multiply-add issue-rate probe: 8 independent mad.wide.u32 accumulation chains per thread, no memory
+	// traffic.  One "limb-MAC" (32 x 32 -> 64 multiply plus 64-bit accumulate) is the unit of the roofline.
+	static __global__ void k_imad_peak(uint64_t* out, int iters, uint32_t seed)
+	{
+		uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
+		uint64_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+#pragma unroll 1
+		for (int i = 0; i < iters; ++i)
+		{
+#pragma unroll
+			for (int u = 0; u < 8; ++u)
+			{
+				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a), "r"(b));
+				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a), "r"(b));
+				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a), "r"(b));
+				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a), "r"(b));
+				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c4) : "r"(a), "r"(b));
+				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c5) : "r"(a), "r"(b));
+				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c6) : "r"(a), "r"(b));
+				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c7) : "r"(a), "r"(b));
+			}
+		}
+		uint64_t s = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+		if (s == 0x1234567ull) out[0] = s;  // keep the chains alive
+	}
+	void launch_imad_peak(uint64_t* out, int iters, uint32_t seed, int blocks, int threads, cudaStream_t st)
+	{
+		k_imad_peak<<<blocks, threads, 0, st>>>(out, iters, seed);
+	}
+}  // namespace qb
+
 struct qb_handle
 {
 	qb::EngineBase* e;

@@ -45,7 +45,8 @@ namespace qb
 #ifdef QB_L
 // ------------------------------------------------------------------------------------------------------------------
 #include "hostmath.hpp"
-#include "kernels.cuh"
+#include "block.cuh"
+#include "launch.cuh"
 
 namespace qb
 {
@@ -92,7 +93,7 @@ namespace qb
 		Rational eps{0, 1};
 		ContextConsts<L> consts;
 		std::map<uint32_t, T> b0_cache;
-		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_fb_in, d_fb_v, d_fb_out, d_fb_terms;
+		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_pv, d_fb_in, d_fb_v, d_fb_out, d_fb_terms;
 		DevCtx cx{};
 		int n_tables = 0, n_jobs = 0;
 		// layout of d_in: [delta | S | P] (tables) then spin; d_jobs: [delta | S | P | b0] (jobs) then spin
@@ -111,7 +112,7 @@ namespace qb
 		~Engine() override
 		{
 			cudaSetDevice(device);
-			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_fb_in, &d_fb_v, &d_fb_out,
+			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_pv, &d_fb_in, &d_fb_v, &d_fb_out,
 			                  &d_fb_terms})
 				b->release();
 			if (stream) cudaStreamDestroy(stream);
@@ -298,7 +299,7 @@ namespace qb
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
-			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) ||
+			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;
 			t_delta = d_in.as<T>();
@@ -334,43 +335,29 @@ namespace qb
 				for (auto& e : ev) QB_CU(cudaEventCreate(&e));
 			if (timing) QB_CU(cudaEventRecord(ev[0], stream));
 			{
-				int threads = 128, total = n_jobs * QB_NCOEF;
-				k_rec_coeffs<L><<<(total + threads - 1) / threads, threads, 0, stream>>>(cx, n_jobs, j_delta, j_spin, j_S, j_P,
-				                                                                         d_coef.as<T>());
+				launch_rec_coeffs<L>(cx, n_jobs, j_delta, j_spin, j_S, j_P, d_coef.as<T>(), stream);
 				++launches;
 				if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
 				if (timing) QB_CU(cudaEventRecord(ev[1], stream));
 			}
 			{
-				int threads = 64;
-				k_series<L><<<(n_jobs + threads - 1) / threads, threads, 0, stream>>>(cx, n_jobs, j_delta, j_spin, j_b0,
-				                                                                      d_coef.as<T>(), d_b.as<T>());
+				launch_polyvals<L>(cx, n_jobs, j_spin, d_coef.as<T>(), d_pv.as<T>(), stream);
+				++launches;
+				launch_series<L>(cx, n_jobs, j_delta, j_spin, j_b0, d_pv.as<T>(), d_b.as<T>(), stream);
 				++launches;
 				if (int rc_ = debug_sync("k_series")) return rc_;
 				if (timing) QB_CU(cudaEventRecord(ev[2], stream));
 			}
 			{
-				int G = 160 / nk;
-				if (G < 1) G = 1;
-				size_t smem = 2 * size_t(G) * nk * sizeof(T);
-				while (smem > 200 * 1024 && G > 1)
-				{
-					--G;
-					smem = 2 * size_t(G) * nk * sizeof(T);
-				}
-				if (smem > 48 * 1024)
-					QB_CU(cudaFuncSetAttribute(k_deriv<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-				int blocks = (n_tables + G - 1) / G;
-				k_deriv<L><<<blocks, G * nk, smem, stream>>>(cx, n_tables, G, d_tref.as<TableRef>(), t_delta, d_b.as<T>(),
-				                                             d_fr.as<T>());
+				launch_pow<L>(cx, n_tables, t_delta, d_pw.as<T>(), stream);
+				++launches;
+				QB_CU(launch_deriv<L>(cx, n_tables, d_tref.as<TableRef>(), t_delta, d_b.as<T>(), d_pw.as<T>(), d_fr.as<T>(), stream));
 				++launches;
 				if (int rc_ = debug_sync("k_deriv")) return rc_;
 				if (timing) QB_CU(cudaEventRecord(ev[3], stream));
 			}
 			{
-				int threads = 64;
-				k_finish<L><<<(n_tables + threads - 1) / threads, threads, 0, stream>>>(cx, n_tables, t_delta, t_spin, t_S, t_P,
-				                                                                        d_fr.as<T>(), d_g.as<T>());
+				launch_finish<L>(cx, n_tables, t_delta, t_spin, t_S, t_P, d_fr.as<T>(), d_g.as<T>(), stream);
 				++launches;
 				if (int rc_ = debug_sync("k_finish")) return rc_;
 				if (timing) QB_CU(cudaEventRecord(ev[4], stream));
@@ -401,12 +388,12 @@ namespace qb
 			cudaEvent_t e0, e1;
 			QB_CU(cudaEventCreate(&e0));
 			QB_CU(cudaEventCreate(&e1));
-			k_imad_peak<<<blocks, threads, 0, stream>>>(d_fb_out.as<uint64_t>(), 64, 12345u);  // warm-up
+			launch_imad_peak(d_fb_out.as<uint64_t>(), 64, 12345u, blocks, threads, stream);  // warm-up
 			double best = 0.0;
 			for (int rep = 0; rep < 5; ++rep)
 			{
 				QB_CU(cudaEventRecord(e0, stream));
-				k_imad_peak<<<blocks, threads, 0, stream>>>(d_fb_out.as<uint64_t>(), iters, 12345u + rep);
+				launch_imad_peak(d_fb_out.as<uint64_t>(), iters, 12345u + rep, blocks, threads, stream);
 				QB_CU(cudaEventRecord(e1, stream));
 				QB_CU(cudaStreamSynchronize(stream));
 				float ms = 0.f;
@@ -458,16 +445,12 @@ namespace qb
 			QB_CU(cudaMemcpyAsync(d_fb_in.p, d, sizeof(T) * size_t(n_d), cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaMemcpyAsync(d_fb_terms.p, terms.data(), sizeof(TermRef) * size_t(m), cudaMemcpyHostToDevice, stream));
 			{
-				int threads = 32;
-				k_vtod<L><<<(n_d + threads - 1) / threads, threads, 0, stream>>>(cx, n_d, d_fb_in.as<T>(), d_fb_v.as<T>());
+				launch_vtod<L>(cx, n_d, d_fb_in.as<T>(), d_fb_v.as<T>(), stream);
 				++launches;
 				if (int rc_ = debug_sync("k_vtod")) return rc_;
 			}
 			{
-				int threads = 128;
-				int64_t total = int64_t(m) * dim_max;
-				k_fblock<L><<<unsigned((total + threads - 1) / threads), threads, 0, stream>>>(
-				    cx, m, dim_max, d_fb_terms.as<TermRef>(), d_g.as<T>(), d_fb_v.as<T>(), d_fb_out.as<T>());
+				launch_fblock<L>(cx, m, dim_max, d_fb_terms.as<TermRef>(), d_g.as<T>(), d_fb_v.as<T>(), d_fb_out.as<T>(), stream);
 				++launches;
 				if (int rc_ = debug_sync("k_fblock")) return rc_;
 			}
@@ -496,8 +479,7 @@ namespace qb
 			if (c) QB_CU(cudaMemcpyAsync(dc, c, rec, cudaMemcpyHostToDevice, stream));
 			if (ia) QB_CU(cudaMemcpyAsync(dia, ia, ints, cudaMemcpyHostToDevice, stream));
 			if (ib) QB_CU(cudaMemcpyAsync(dib, ib, ints, cudaMemcpyHostToDevice, stream));
-			k_ops<L><<<(n + 63) / 64, 64, 0, stream>>>(cx, op, n, a ? da : nullptr, b ? db : nullptr, c ? dc : nullptr,
-			                                           ia ? dia : nullptr, ib ? dib : nullptr, dout);
+			launch_ops<L>(cx, op, n, a ? da : nullptr, b ? db : nullptr, c ? dc : nullptr, ia ? dia : nullptr, ib ? dib : nullptr, dout, stream);
 			++launches;
 			QB_CU(cudaGetLastError());
 			QB_CU(cudaMemcpyAsync(out, dout, rec, cudaMemcpyDeviceToHost, stream));

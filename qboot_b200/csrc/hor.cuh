@@ -13,6 +13,7 @@
 // limb routine addresses one memory space only.
 #pragma once
 
+#include "fastops.cuh"
 #include "mpf.cuh"
 
 namespace qb
@@ -222,8 +223,8 @@ namespace qb
 		copy(s, c[deg]);
 		for (int d = deg - 1; d >= 0; --d)
 		{
-			mul_si(s, s, int64_t(n), prec);
-			add(s, s, c[d], prec);
+			fast::mul_small(s, s, int64_t(n), prec);
+			fast::add(s, s, c[d], prec);
 		}
 	}
 
@@ -243,7 +244,7 @@ namespace qb
 				if (uint32_t(i) <= n)
 				{
 					poly_eval_ui(pv, lc + i * st, deg, n, prec);
-					fma(sum, pv, hist[(n - uint32_t(i)) & 7u], sum, prec);
+					fast::fma(sum, pv, hist[(n - uint32_t(i)) & 7u], sum, prec);
 				}
 			neg(sum);
 			poly_eval_ui(pv, lc, deg, n, prec);

@@ -1,6 +1,7 @@
 // qboot_b200 -- CUDA kernels of the block-table pipeline (sm_100a), templated on the limb count L.
 //
 //   k_rec_coeffs   one thread per (series job, recurrence coefficient)        -> coef[job][40]
+//   k_polyvals     one thread per (series job, n): the recurrence polynomials at n  -> pv[job][n][8]
 //   k_series       one thread per series job, n_max sequential steps          -> b[job][0..n_max]
 //   k_deriv        one CTA per G tables, (lambda+1) Horner chains per table running as a software pipeline through
 //                  shared memory (chain k consumes the coefficient chain k-1 scaled one step earlier) -> fr[table][k]
@@ -18,33 +19,11 @@
 
 #define QB_TABLE_QUAL static __device__
 #include "block.cuh"
+#include "launch.cuh"
 #include "hor_table.inc"
 
 namespace qb
 {
-	// device-resident context constants (see qb_context_init)
-	struct DevCtx
-	{
-		int prec;
-		uint32_t n_max, lambda;
-		Rational eps;
-		const uint32_t* rho;      // mpf<L>
-		const uint32_t* mat;      // (lambda+1)^2 mpf<L>, row-major
-		const uint32_t* ln2e;     // mpf<L + QB_EXT_LIMBS>
-		const uint32_t* ln4e;
-		const uint32_t* lnrhoe;
-		const uint32_t* kfact;    // k!, k = 0..lambda, mpf<L>
-	};
-
-	// a series job: one run of the recurrence at (Delta', spin, S, P)
-	// a table: references one job, or two for a divergent operator (averaged, src/hor_recursion.cpp:21-28)
-	struct TableRef
-	{
-		int32_t job0, job1;  // job1 < 0: single
-	};
-
-	constexpr int QB_NCOEF = 40;  // 8 polynomials x 5 coefficients (spin 0 uses 6 x 4 of them)
-
 	template <int L>
 	__global__ void k_rec_coeffs(DevCtx cx, int n_jobs, const mpf<L>* __restrict__ delta, const uint32_t* __restrict__ spin,
 	                             const mpf<L>* __restrict__ S, const mpf<L>* __restrict__ P, mpf<L>* __restrict__ coef)
@@ -77,9 +56,39 @@ namespace qb
 		for (int k = 0; k < st; ++k) copy(out[i * st + k], pe[k]);
 	}
 
+	// values of the K recurrence polynomials at every n: pv[(job * n_max + n - 1) * 8 + i] = p_i(n), by Horner with the
+	// integer n (include/qboot/algebra/polynomial.hpp:66-83).  They do not depend on the series, so they are taken off its
+	// sequential chain: one thread per (job, n).
+	template <int L>
+	__global__ void k_polyvals(DevCtx cx, int n_jobs, const uint32_t* __restrict__ spin, const mpf<L>* __restrict__ coef,
+	                           mpf<L>* __restrict__ pv)
+	{
+		const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+		const int job = int(gid / cx.n_max);
+		const uint32_t n = uint32_t(gid % cx.n_max) + 1u;
+		if (job >= n_jobs) return;
+		const uint32_t sp = spin[job];
+		const int K = sp == 0 ? 6 : 8, deg = sp == 0 ? 3 : 4, st = deg + 1;
+		const mpf<L>* c = coef + size_t(job) * QB_NCOEF;
+		mpf<L>* out = pv + size_t(gid) * 8;
+		for (int i = 0; i < K; ++i)
+		{
+			mpf<L> s;
+			copy(s, c[i * st + deg]);
+			for (int d = deg - 1; d >= 0; --d)
+			{
+				fast::mul_small(s, s, int64_t(n), cx.prec);
+				fast::add(s, s, c[i * st + d], cx.prec);
+			}
+			copy(out[i], s);
+		}
+	}
+
+	// b[n] = -(sum_{i=1}^{min(n,K-1)} p_i(n) b[n-i]) / p_0(n), one thread per series job (src/hor_recursion.cpp:31-37).
+	// The running sum stays in registers; p_i(n) and the previous terms are read where they lie in global memory.
 	template <int L>
 	__global__ void k_series(DevCtx cx, int n_jobs, const mpf<L>* __restrict__ delta, const uint32_t* __restrict__ spin,
-	                         const mpf<L>* __restrict__ b0, const mpf<L>* __restrict__ coef, mpf<L>* __restrict__ b)
+	                         const mpf<L>* __restrict__ b0, const mpf<L>* __restrict__ pv, mpf<L>* __restrict__ b)
 	{
 		int job = blockIdx.x * blockDim.x + threadIdx.x;
 		if (job >= n_jobs) return;
@@ -91,95 +100,141 @@ namespace qb
 			for (uint32_t n = 1; n <= cx.n_max; ++n) set_zero(bj[n]);
 			return;
 		}
-		series<L>(bj, 1, cx.n_max, coef + size_t(job) * QB_NCOEF, spin[job], cx.prec);
+		const int K = spin[job] == 0 ? 6 : 8;
+		const int prec = cx.prec;
+		const mpf<L>* pj = pv + size_t(job) * cx.n_max * 8;
+		for (uint32_t n = 1; n <= cx.n_max; ++n)
+		{
+			const mpf<L>* p = pj + size_t(n - 1) * 8;
+			mpf<L> sum, bn;
+			fast::mul(sum, p[1], bj[n - 1], prec);  // fma(0, p_1 b[n-1]) rounds like the product
+			for (int i = 2; i < K; ++i)
+				if (uint32_t(i) <= n) fast::fma(sum, p[i], bj[n - uint32_t(i)], sum, prec);
+			neg(sum);
+			fast::div(bn, sum, p[0], prec);
+			copy(bj[n], bn);
+		}
 	}
 
-	// shared-memory pipeline of the lambda+1 derivative chains
+	// powers of one table: pw[t][0] = 4^Delta (src/hor_recursion.cpp:43), pw[t][1 + k] = rho^(q_k) with q_k = Delta - k by
+	// k rounded decrements (include/qboot/algebra/real_function.hpp:239,262); one thread per power
 	template <int L>
-	__global__ void k_deriv(DevCtx cx, int n_tables, int G, const TableRef* __restrict__ tref,
-	                        const mpf<L>* __restrict__ delta, const mpf<L>* __restrict__ b, mpf<L>* __restrict__ fr)
+	__global__ void k_pow(DevCtx cx, int n_tables, const mpf<L>* __restrict__ delta, mpf<L>* __restrict__ pw)
+	{
+		constexpr int E = L + QB_EXT_LIMBS;
+		const int np = int(cx.lambda) + 2;
+		int gid = blockIdx.x * blockDim.x + threadIdx.x;
+		int t = gid / np, j = gid % np;
+		if (t >= n_tables) return;
+		mpf<L> q, r;
+		copy(q, delta[t]);
+		for (int i = 1; i < j; ++i) add_si(q, q, -1, cx.prec);
+		if (j == 0)
+			pow_from_log<L>(r, *reinterpret_cast<const mpf<E>*>(cx.ln4e), q, *reinterpret_cast<const mpf<E>*>(cx.ln2e), cx.prec);
+		else
+			pow_from_log<L>(r, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe), q, *reinterpret_cast<const mpf<E>*>(cx.ln2e), cx.prec);
+		copy(pw[size_t(t) * np + j], r);
+	}
+
+	// shared-memory record with an odd word stride (conflict-free when every thread walks its own record)
+	template <int L>
+	struct SRec
+	{
+		static constexpr int W = L + 2;
+		static constexpr int SW = (W % 2 == 0) ? W + 1 : W;
+		static __device__ __forceinline__ mpf<L>& at(uint32_t* base, int idx) { return *reinterpret_cast<mpf<L>*>(base + size_t(idx) * SW); }
+	};
+
+	// Shared-memory pipeline of the lambda+1 derivative chains.  One CTA = G tables x (lambda+1) threads; thread (g, k) owns
+	// chain k of table g.  At step tau it takes coefficient a_{k-1}[n] (n = n_max - tau + k) that chain k-1 produced one
+	// step earlier (double-buffered in shared memory), scales it to a_k[n] = a_{k-1}[n] * (q_{k-1} + n), and feeds its Horner
+	// sum s_k <- s_k * rho + a_k[n].  All per-thread state (Horner sum, q_{k-1}) lives in shared memory; the limb arithmetic
+	// itself runs in registers (fastops.cuh), so the stack is touched only on the rare generic fallbacks.
+	template <int L>
+	__global__ void __launch_bounds__(192, 2)
+	    k_deriv(DevCtx cx, int n_tables, int G, const TableRef* __restrict__ tref, const mpf<L>* __restrict__ delta,
+	            const mpf<L>* __restrict__ b, const mpf<L>* __restrict__ pw, mpf<L>* __restrict__ fr)
 	{
 		extern __shared__ uint32_t smem_raw[];
-		constexpr int E = L + QB_EXT_LIMBS;
+		using SR = SRec<L>;
 		const int nk = int(cx.lambda) + 1;
-		const int g = threadIdx.x / nk, k = threadIdx.x % nk;
+		const int T = G * nk;
+		const int tid = threadIdx.x;
+		const int g = tid / nk, k = tid % nk;
 		const int t = blockIdx.x * G + g;
 		const bool active = (g < G) && (t < n_tables);
-		mpf<L>* buf0 = reinterpret_cast<mpf<L>*>(smem_raw);
-		mpf<L>* buf1 = buf0 + G * nk;
+		uint32_t* buf0 = smem_raw;
+		uint32_t* buf1 = buf0 + size_t(T) * SR::SW;
+		uint32_t* accS = buf1 + size_t(T) * SR::SW;   // Horner sums
+		uint32_t* accQ = accS + size_t(T) * SR::SW;   // q_{k-1}
+		uint32_t* c4s = accQ + size_t(T) * SR::SW;    // 4^Delta per table
+		uint32_t* rhos = c4s + size_t(G) * SR::SW;    // rho
 		const int prec = cx.prec;
 		const uint32_t n_max = cx.n_max;
-
-		mpf<L> rho, q, qprev, s, a, ap, c4, rp, tmp;
-		copy(rho, *reinterpret_cast<const mpf<L>*>(cx.rho));
 		const mpf<L>* b0p = nullptr;
 		const mpf<L>* b1p = nullptr;
-		set_zero(s);
-		set_zero(c4);
-		set_zero(rp);
-		set_zero(q);
-		set_zero(qprev);
+		if (tid == 0) copy(SR::at(rhos, 0), *reinterpret_cast<const mpf<L>*>(cx.rho));
 		if (active)
 		{
-			// q_k = Delta - k by k rounded decrements                      (real_function.hpp:239 `pow_ -= 1`)
+			// q_{k-1} = Delta - (k-1) by rounded decrements                 (real_function.hpp:239 `pow_ -= 1`)
+			mpf<L> q;
 			copy(q, delta[t]);
-			copy(qprev, q);
-			for (int j = 0; j < k; ++j)
-			{
-				copy(qprev, q);
-				add_si(q, q, -1, prec);
-			}
+			for (int j = 0; j + 1 < k; ++j) add_si(q, q, -1, prec);
+			copy(SR::at(accQ, tid), q);
+			set_zero(SR::at(accS, tid));
+			if (k == 0) copy(SR::at(c4s, g), pw[size_t(t) * (nk + 1)]);
 			TableRef tr = tref[t];
 			b0p = b + size_t(tr.job0) * (n_max + 1);
 			b1p = tr.job1 >= 0 ? b + size_t(tr.job1) * (n_max + 1) : nullptr;
-			if (k == 0)
-				pow_from_log<L>(c4, *reinterpret_cast<const mpf<E>*>(cx.ln4e), q, *reinterpret_cast<const mpf<E>*>(cx.ln2e),
-				                prec);  // 4^Delta
-			else
-				pow_from_log<L>(rp, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe), q, *reinterpret_cast<const mpf<E>*>(cx.ln2e),
-				                prec);  // rho^(q_k)
 		}
+		__syncthreads();
+		const mpf<L>& rho = SR::at(rhos, 0);
+		mpf<L>& s = SR::at(accS, tid);
 		const int steps = int(n_max) + nk;
 		for (int tau = 0; tau < steps; ++tau)
 		{
-			mpf<L>* cur = (tau & 1) ? buf1 : buf0;
-			mpf<L>* prv = (tau & 1) ? buf0 : buf1;
+			uint32_t* cur = (tau & 1) ? buf1 : buf0;
+			uint32_t* prv = (tau & 1) ? buf0 : buf1;
 			int idx = tau - k;  // 0 .. n_max  <->  n = n_max - idx
 			if (active && idx >= 0 && idx <= int(n_max))
 			{
 				uint32_t n = n_max - uint32_t(idx);
+				mpf<L>& a = SR::at(cur, tid);
 				if (k == 0)
 				{
-					copy(ap, b0p[n]);
 					if (b1p)
 					{
-						copy(tmp, b1p[n]);
-						add(ap, ap, tmp, prec);
-						mul_2si(ap, ap, -1);
+						// divergent operator: average of the two shifted series           (hor_recursion.cpp:23-27)
+						mpf<L> u, v;
+						copy(u, b0p[n]);
+						copy(v, b1p[n]);
+						add(u, u, v, prec);
+						mul_2si(u, u, -1);
+						fast::mul(a, u, SR::at(c4s, g), prec);
 					}
-					mul(a, ap, c4, prec);                                      // h *= 4^Delta (hor_recursion.cpp:43)
+					else
+						fast::mul(a, b0p[n], SR::at(c4s, g), prec);                  // h *= 4^Delta (hor_recursion.cpp:43)
 				}
 				else
 				{
-					copy(ap, prv[g * nk + k - 1]);
-					deriv_scale(a, ap, qprev, n, prec);
+					mpf<L> f;
+					fast::add_small(f, SR::at(accQ, tid), int64_t(n), prec);         // q_{k-1} + n
+					fast::mul(a, SR::at(prv, tid - 1), f, prec);                     // derivate (real_function.hpp:236-240)
 				}
 				if (idx == 0)
 					copy(s, a);
 				else
-					deriv_horner(s, rho, a, prec);
-				copy(cur[g * nk + k], a);
+					fast::fma(s, s, rho, a, prec);                                   // Horner (real_function.hpp:248-259)
 			}
 			__syncthreads();
 		}
 		if (active)
 		{
-			if (k == 0)
-				pow_from_log<L>(rp, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe), q, *reinterpret_cast<const mpf<E>*>(cx.ln2e),
-				                prec);
-			mpf<L> kf, f;
+			mpf<L> sl, rp, kf, f;
+			copy(sl, s);
+			copy(rp, pw[size_t(t) * (nk + 1) + 1 + k]);
 			copy(kf, reinterpret_cast<const mpf<L>*>(cx.kfact)[k]);
-			deriv_finish(f, s, rp, kf, uint32_t(k), prec);
+			deriv_finish(f, sl, rp, kf, uint32_t(k), prec);
 			copy(fr[size_t(t) * nk + k], f);
 		}
 	}
@@ -216,11 +271,6 @@ namespace qb
 		v_to_d_table(v + size_t(i) * cf_dim(int(cx.lambda)), 1, int(cx.lambda), d[i], p4, cx.prec);
 	}
 
-	// term = (table index, d index, sym); output packed per term at out[out_ofs ...]
-	struct TermRef
-	{
-		int32_t table, dix, sym, out_ofs;
-	};
 	template <int L>
 	__global__ void k_fblock(DevCtx cx, int n_terms, int dim_max, const TermRef* __restrict__ terms,
 	                         const mpf<L>* __restrict__ g, const mpf<L>* __restrict__ v, mpf<L>* __restrict__ out)
@@ -288,6 +338,13 @@ namespace qb
 			break;
 		case 18: si_sub(r, p, x, prec); break;
 		case 20: sub_q(r, x, p, uint32_t(q), prec); break;
+		case 40: fast::mul(r, x, y, prec); break;
+		case 41: fast::fma(r, x, y, z, prec); break;
+		case 42: fast::add(r, x, y, prec); break;
+		case 43: fast::add(r, x, y, prec, true); break;
+		case 44: fast::mul_small(r, x, p, prec); break;
+		case 45: fast::add_small(r, x, p, prec); break;
+		case 46: fast::div(r, x, y, prec); break;
 		case 23: r.sk = uint32_t(cmp(x, y) + 1); break;
 		case 24: r.sk = is_integer(x) ? 1u : 0u; break;
 		default: set_nan(r); break;
@@ -295,29 +352,4 @@ namespace qb
 		copy(out[i], r);
 	}
 
-	// Integer multiply-add issue-rate probe: 8 independent mad.wide.u32 accumulation chains per thread, no memory
-	// traffic.  One "limb-MAC" (32 x 32 -> 64 multiply plus 64-bit accumulate) is the unit of the roofline.
-	static __global__ void k_imad_peak(uint64_t* out, int iters, uint32_t seed)
-	{
-		uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
-		uint64_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
-#pragma unroll 1
-		for (int i = 0; i < iters; ++i)
-		{
-#pragma unroll
-			for (int u = 0; u < 8; ++u)
-			{
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c4) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c5) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c6) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c7) : "r"(a), "r"(b));
-			}
-		}
-		uint64_t s = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
-		if (s == 0x1234567ull) out[0] = s;  // keep the chains alive
-	}
 }  // namespace qb

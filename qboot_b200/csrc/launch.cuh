@@ -1,0 +1,65 @@
+// qboot_b200 -- launch interface between the per-precision engine (host code, engine.cuh) and the kernel translation
+// units (kernel_inst.cu, one per limb count and kernel group so that the heavy device code compiles in parallel).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "hor.cuh"
+
+namespace qb
+{
+	// device-resident context constants (see qb_context_init)
+	struct DevCtx
+	{
+		int prec;
+		uint32_t n_max, lambda;
+		Rational eps;
+		const uint32_t* rho;      // mpf<L>
+		const uint32_t* mat;      // (lambda+1)^2 mpf<L>, row-major
+		const uint32_t* ln2e;     // mpf<L + QB_EXT_LIMBS>
+		const uint32_t* ln4e;
+		const uint32_t* lnrhoe;
+		const uint32_t* kfact;    // k!, k = 0..lambda, mpf<L>
+	};
+
+	// a series job: one run of the recurrence at (Delta', spin, S, P)
+	// a table: references one job, or two for a divergent operator (averaged, src/hor_recursion.cpp:21-28)
+	struct TableRef
+	{
+		int32_t job0, job1;  // job1 < 0: single
+	};
+	// F/H term = (table index, d index, sym); output packed per term at out[out_ofs ...]
+	struct TermRef
+	{
+		int32_t table, dix, sym, out_ofs;
+	};
+
+	constexpr int QB_NCOEF = 40;  // 8 polynomials x 5 coefficients (spin 0 uses 6 x 4 of them)
+
+	template <int L>
+	void launch_rec_coeffs(const DevCtx& cx, int n_jobs, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* S,
+	                       const mpf<L>* P, mpf<L>* coef, cudaStream_t st);
+	template <int L>
+	void launch_polyvals(const DevCtx& cx, int n_jobs, const uint32_t* spin, const mpf<L>* coef, mpf<L>* pv, cudaStream_t st);
+	template <int L>
+	void launch_series(const DevCtx& cx, int n_jobs, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* b0,
+	                   const mpf<L>* pv, mpf<L>* b, cudaStream_t st);
+	template <int L>
+	cudaError_t launch_deriv(const DevCtx& cx, int n_tables, const TableRef* tref, const mpf<L>* delta, const mpf<L>* b,
+	                         const mpf<L>* pw, mpf<L>* fr, cudaStream_t st);
+	template <int L>
+	void launch_pow(const DevCtx& cx, int n_tables, const mpf<L>* delta, mpf<L>* pw, cudaStream_t st);
+	template <int L>
+	void launch_finish(const DevCtx& cx, int n_tables, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* S,
+	                   const mpf<L>* P, const mpf<L>* fr, mpf<L>* g, cudaStream_t st);
+	template <int L>
+	void launch_vtod(const DevCtx& cx, int n_d, const mpf<L>* d, mpf<L>* v, cudaStream_t st);
+	template <int L>
+	void launch_fblock(const DevCtx& cx, int n_terms, int dim_max, const TermRef* terms, const mpf<L>* g, const mpf<L>* v,
+	                   mpf<L>* out, cudaStream_t st);
+	template <int L>
+	void launch_ops(const DevCtx& cx, int op, int n, const mpf<L>* a, const mpf<L>* b, const mpf<L>* c, const int64_t* ia,
+	                const int64_t* ib, mpf<L>* out, cudaStream_t st);
+	// integer multiply-add probe (capi.cu)
+	void launch_imad_peak(uint64_t* out, int iters, uint32_t seed, int blocks, int threads, cudaStream_t st);
+}  // namespace qb

@@ -7,6 +7,7 @@
 // rounding equals the correct rounding unless the exact value lies within that distance of a rounding boundary.
 #pragma once
 
+#include "fastops.cuh"
 #include "mpf.cuh"
 
 #ifndef QB_EXT_LIMBS
@@ -87,13 +88,13 @@ namespace qb
 		{
 			if (is_zero(term)) break;
 			if (term.exp < -pe - 4) break;
-			add(sum, sum, term, pe);
-			mul(u, term, x, pe);
+			fast::add(sum, sum, term, pe);
+			fast::mul(u, term, x, pe);
 			div_si(term, u, n + 1, pe);
 		}
 		for (int i = 0; i < s; ++i)
 		{
-			mul(u, sum, sum, pe);
+			fast::mul(u, sum, sum, pe);
 			copy(sum, u);
 		}
 		copy(r, sum);
@@ -112,7 +113,7 @@ namespace qb
 		copy(lx, lnx);
 		copy(l2, ln2);
 		widen(ye, y);
-		mul(t, ye, lx, 32 * E);
+		fast::mul(t, ye, lx, 32 * E);
 		exp_ext(v, t, l2);
 		narrow(r, v, prec);
 	}

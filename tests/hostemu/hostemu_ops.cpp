@@ -6,6 +6,7 @@
 
 #include "../../qboot_b200/csrc/mpf.cuh"
 #include "../../qboot_b200/csrc/mpf_math.cuh"
+#include "../../qboot_b200/csrc/fastops.cuh"
 
 namespace
 {
@@ -48,6 +49,13 @@ namespace
 			case 22: qb::set_ui_2exp(r, uint64_t(p), int32_t(q), prec); break;
 			case 23: r.sk = uint32_t(qb::cmp(x, y) + 1); break;
 			case 24: r.sk = qb::is_integer(x) ? 1u : 0u; break;
+			case 40: qb::fast::mul(r, x, y, prec); break;
+			case 41: qb::fast::fma(r, x, y, z, prec); break;
+			case 42: qb::fast::add(r, x, y, prec); break;
+			case 43: qb::fast::add(r, x, y, prec, true); break;
+			case 44: qb::fast::mul_small(r, x, p, prec); break;
+			case 45: qb::fast::add_small(r, x, p, prec); break;
+			case 46: qb::fast::div(r, x, y, prec); break;
 			case 13:  // pow(x, y) with x > 0 given ln(x) in consts (extended precision)
 			case 14:  // ui_pow
 			case 15:  // exp
