@@ -20,8 +20,8 @@ ROOT = os.path.dirname(HERE)
 BUILD = os.path.join(ROOT, "build", "qb")
 LIB = os.path.join(HERE, "libqboot_b200.so")
 
-# limb counts compiled in: 600, 800, 1000/1024, 1536 bits (override: QB_LIMBS=19,32)
-LIMBS = tuple(int(x) for x in os.environ.get("QB_LIMBS", "19,25,32,48").split(","))
+# limb counts compiled in: 512, 600, 800, 1000/1024, 1200, 1536 bits (override: QB_LIMBS=19,32)
+LIMBS = tuple(int(x) for x in os.environ.get("QB_LIMBS", "16,19,25,32,38,48").split(","))
 KGROUPS = (0, 1, 2, 3, 4)
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -106,55 +106,55 @@ namespace qb
 #define QB_LOADF(mm, nn) copy(h, f[int64_t(cf_index(lambda, (mm), (nn))) * fs])
 		// h[m + 2, n - 1]
 		QB_LOADF(m + 2, n - 1);
-		mul_si(val, h, -int64_t(m + 1) * (m + 2), prec);
+		fast::mul_small(val, h, -int64_t(m + 1) * (m + 2), prec);
 		// h[m + 1, n - 1]
 		add_q(term, S, eps.num, eps.den, prec);
-		mul_si(term, term, 2, prec);
-		add_si(term, term, -int64_t(m + 4 * n - 6), prec);
-		mul_si(term, term, 2 * (m + 1), prec);
+		fast::mul_small(term, term, 2, prec);
+		fast::add_small(term, term, -int64_t(m + 4 * n - 6), prec);
+		fast::mul_small(term, term, 2 * (m + 1), prec);
 		QB_LOADF(m + 1, n - 1);
-		mul(term, term, h, prec);
-		add(val, val, term, prec);
+		fast::mul(term, term, h, prec);
+		fast::add(val, val, term, prec);
 		// h[m, n - 1]
 		set_q(term, eps.num * int64_t(4 * (m + n - 1)), eps.den, prec);
-		add_si(term, term, int64_t(m) * (m + 8 * n - 5) + int64_t(n) * (4 * n - 2) - 2, prec);
-		mul_si(t2, P, 2, prec);
-		add(term, term, t2, prec);
-		mul_si(t2, S, int64_t(8 * n + 4 * m - 8), prec);
-		add(term, term, t2, prec);
-		add(term, term, qc4, prec);
-		mul_si(term, term, 4, prec);
+		fast::add_small(term, term, int64_t(m) * (m + 8 * n - 5) + int64_t(n) * (4 * n - 2) - 2, prec);
+		fast::mul_small(t2, P, 2, prec);
+		fast::add(term, term, t2, prec);
+		fast::mul_small(t2, S, int64_t(8 * n + 4 * m - 8), prec);
+		fast::add(term, term, t2, prec);
+		fast::add(term, term, qc4, prec);
+		fast::mul_small(term, term, 4, prec);
 		QB_LOADF(m, n - 1);
-		mul(term, term, h, prec);
-		add(val, val, term, prec);
+		fast::mul(term, term, h, prec);
+		fast::add(val, val, term, prec);
 		// h[m - 1, n - 1]
 		if (m >= 1)
 		{
 			set_q(term, eps.num * int64_t(2 * (m + 1 - 2 * n)), eps.den, prec);
-			add_si(term, term, int64_t(m) * (m + 12 * n - 13) + int64_t(n) * (12 * n - 34) + 22, prec);
-			mul_si(t2, P, 2, prec);
-			add(term, term, t2, prec);
-			mul_si(t2, S, int64_t(8 * n + 2 * m - 10), prec);
-			add(term, term, t2, prec);
-			mul_si(term, term, 8, prec);
+			fast::add_small(term, term, int64_t(m) * (m + 12 * n - 13) + int64_t(n) * (12 * n - 34) + 22, prec);
+			fast::mul_small(t2, P, 2, prec);
+			fast::add(term, term, t2, prec);
+			fast::mul_small(t2, S, int64_t(8 * n + 2 * m - 10), prec);
+			fast::add(term, term, t2, prec);
+			fast::mul_small(term, term, 8, prec);
 			QB_LOADF(m - 1, n - 1);
-			mul(term, term, h, prec);
-			add(val, val, term, prec);
+			fast::mul(term, term, h, prec);
+			fast::add(val, val, term, prec);
 		}
 		// h[m + 1, n - 2] and h[m + 2, n - 2]
 		if (n >= 2)
 		{
 			set_q(term, -2 * eps.num, eps.den, prec);
-			add_si(term, term, int64_t(3 * m + 4 * n - 6), prec);
-			mul_si(t2, S, 2, prec);
-			add(term, term, t2, prec);
-			mul_si(term, term, int64_t(8 * (m + 1)), prec);
+			fast::add_small(term, term, int64_t(3 * m + 4 * n - 6), prec);
+			fast::mul_small(t2, S, 2, prec);
+			fast::add(term, term, t2, prec);
+			fast::mul_small(term, term, int64_t(8 * (m + 1)), prec);
 			QB_LOADF(m + 1, n - 2);
-			mul(term, term, h, prec);
+			fast::mul(term, term, h, prec);
 			QB_LOADF(m + 2, n - 2);
-			mul_si(t2, h, int64_t(4 * (m + 1) * (m + 2)), prec);
-			add(term, term, t2, prec);
-			add(val, val, term, prec);
+			fast::mul_small(t2, h, int64_t(4 * (m + 1) * (m + 2)), prec);
+			fast::add(term, term, t2, prec);
+			fast::add(val, val, term, prec);
 		}
 #undef QB_LOADF
 		// common_factor = 4 n eps + (4 n - 2) n
@@ -171,20 +171,20 @@ namespace qb
 		set_zero(term);
 		if (m >= 3)
 		{
-			mul_si(t2, p3, 8, prec);
-			add(term, term, t2, prec);
+			fast::mul_small(t2, p3, 8, prec);
+			fast::add(term, term, t2, prec);
 		}
 		if (m >= 2)
 		{
-			mul_si(t2, p2, 4, prec);
-			add(term, term, t2, prec);
+			fast::mul_small(t2, p2, 4, prec);
+			fast::add(term, term, t2, prec);
 		}
 		if (m >= 1)
 		{
-			mul_si(t2, p1, 2, prec);
-			sub(term, term, t2, prec);
+			fast::mul_small(t2, p1, 2, prec);
+			fast::add(term, term, t2, prec, true);
 		}
-		add(out, val, term, prec);
+		fast::add(out, val, term, prec);
 	}
 	// whole table, serial: f (anywhere) row 0 (dx = 0..lambda) must be filled; D, S, P anywhere
 	template <int L>

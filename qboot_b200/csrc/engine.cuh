@@ -93,7 +93,7 @@ namespace qb
 		Rational eps{0, 1};
 		ContextConsts<L> consts;
 		std::map<uint32_t, T> b0_cache;
-		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_pv, d_fb_in, d_fb_v, d_fb_out, d_fb_terms;
+		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_pv, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms;
 		DevCtx cx{};
 		int n_tables = 0, n_jobs = 0;
 		// layout of d_in: [delta | S | P] (tables) then spin; d_jobs: [delta | S | P | b0] (jobs) then spin
@@ -112,7 +112,7 @@ namespace qb
 		~Engine() override
 		{
 			cudaSetDevice(device);
-			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_pv, &d_fb_in, &d_fb_v, &d_fb_out,
+			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_pv, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
 			                  &d_fb_terms})
 				b->release();
 			if (stream) cudaStreamDestroy(stream);
@@ -299,7 +299,7 @@ namespace qb
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
-			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) ||
+			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * n1 * (size_t(n_max) + 1) * nt) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;
 			t_delta = d_in.as<T>();
@@ -351,7 +351,9 @@ namespace qb
 			{
 				launch_pow<L>(cx, n_tables, t_delta, d_pw.as<T>(), stream);
 				++launches;
-				QB_CU(launch_deriv<L>(cx, n_tables, d_tref.as<TableRef>(), t_delta, d_b.as<T>(), d_pw.as<T>(), d_fr.as<T>(), stream));
+				launch_scale<L>(cx, n_tables, d_tref.as<TableRef>(), t_delta, d_b.as<T>(), d_pw.as<T>(), d_a.as<T>(), stream);
+				++launches;
+				launch_horner<L>(cx, n_tables, d_a.as<T>(), d_pw.as<T>(), d_fr.as<T>(), stream);
 				++launches;
 				if (int rc_ = debug_sync("k_deriv")) return rc_;
 				if (timing) QB_CU(cudaEventRecord(ev[3], stream));

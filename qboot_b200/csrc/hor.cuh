@@ -49,7 +49,7 @@ namespace qb
 			if (c == 1)
 				copy(t, D);
 			else
-				mul_si(t, D, c, prec);
+				fast::mul_small(t, D, c, prec);
 			--nD;
 		}
 		else if (nS)
@@ -57,7 +57,7 @@ namespace qb
 			if (c == 1)
 				copy(t, S);
 			else
-				mul_si(t, S, c, prec);
+				fast::mul_small(t, S, c, prec);
 			--nS;
 		}
 		else if (nP)
@@ -65,7 +65,7 @@ namespace qb
 			if (c == 1)
 				copy(t, P);
 			else
-				mul_si(t, P, c, prec);
+				fast::mul_small(t, P, c, prec);
 			--nP;
 		}
 		else if (nl)
@@ -80,11 +80,23 @@ namespace qb
 			set_q(t, c * eps.num, eps.den, prec);
 			--ne;
 		}
-		for (; nD > 0; --nD) mul(t, t, D, prec);
-		for (; nS > 0; --nS) mul(t, t, S, prec);
-		for (; nP > 0; --nP) mul(t, t, P, prec);
-		for (; nl > 0; --nl) mul_si(t, t, int64_t(spin), prec);
-		for (; ne > 0; --ne) mul_q(t, t, eps.num, eps.den, prec);
+		for (; nD > 0; --nD) fast::mul(t, t, D, prec);
+		for (; nS > 0; --nS) fast::mul(t, t, S, prec);
+		for (; nP > 0; --nP) fast::mul(t, t, P, prec);
+		for (; nl > 0; --nl) fast::mul_small(t, t, int64_t(spin), prec);
+		for (; ne > 0; --ne)
+		{
+			// eps = +-1 / 2^k (dimensions 3, 2.5, ...): the rounded product is an exact exponent shift
+			if ((eps.num == 1 || eps.num == -1) && (eps.den & (eps.den - 1)) == 0 && kind(t) == K_REG)
+			{
+				int sh = 0;
+				while ((eps.den >> sh) > 1u) ++sh;
+				t.exp -= sh;
+				if (eps.num < 0) t.sk ^= SIGN_BIT;
+			}
+			else
+				mul_q(t, t, eps.num, eps.den, prec);
+		}
 	}
 
 	// one coefficient a[i][d]; r, D, S, P thread-local, the tables anywhere
@@ -102,9 +114,9 @@ namespace qb
 			{
 				HorMono mo = monos[po.first + k];
 				hor_monomial(t, mo, false, D, S, P, spin, eps, prec);
-				add(acc, acc, t, prec, mo.c < 0);
+				fast::add(acc, acc, t, prec, mo.c < 0);
 			}
-			add_si(acc, acc, po.konst, prec);
+			fast::add_small(acc, acc, po.konst, prec);
 		}
 		if (po.flag == 1)
 		{
@@ -127,8 +139,8 @@ namespace qb
 	{
 		// in place, top down: new[m+1] = c[m]; new[i] = c[i] * a + c[i-1]; new[0] = c[0] * a
 		copy(c[m + 1], c[m]);
-		for (int i = m; i >= 1; --i) fma(c[i], c[i], a, c[i - 1], prec);
-		mul(c[0], c[0], a, prec);
+		for (int i = m; i >= 1; --i) fast::fma(c[i], c[i], a, c[i - 1], prec);
+		fast::mul(c[0], c[0], a, prec);
 	}
 
 	// p_0 (first == true) or p_{K-1}: products of linear factors (n + a), built by repeated mul_linear exactly as the

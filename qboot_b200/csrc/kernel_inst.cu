@@ -1,5 +1,5 @@
 // qboot_b200 -- kernel translation unit: nvcc -DQB_L=<limbs> -DQB_KGROUP=<0..4> kernel_inst.cu
-//   group 0: k_rec_coeffs, k_polyvals, k_ops    1: k_series    2: k_deriv    3: k_finish    4: k_vtod, k_fblock, k_pow
+//   group 0: k_rec_coeffs, k_polyvals, k_ops    1: k_series    2: k_scale, k_horner    3: k_finish    4: k_vtod, k_fblock, k_pow
 #if !defined(QB_L) || !defined(QB_KGROUP)
 #error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..4>"
 #endif
@@ -39,24 +39,20 @@ namespace qb
 	}
 #elif QB_KGROUP == 2
 	template <>
-	cudaError_t launch_deriv<QB_L>(const DevCtx& cx, int n_tables, const TableRef* tref, const mpf<QB_L>* delta,
-	                               const mpf<QB_L>* b, const mpf<QB_L>* pw, mpf<QB_L>* fr, cudaStream_t st)
+	void launch_scale<QB_L>(const DevCtx& cx, int n_tables, const TableRef* tref, const mpf<QB_L>* delta, const mpf<QB_L>* b,
+	                        const mpf<QB_L>* pw, mpf<QB_L>* a, cudaStream_t st)
 	{
-		const int nk = int(cx.lambda) + 1;
-		using SR = SRec<QB_L>;
-		int G = 160 / nk;
-		if (G < 1) G = 1;
-		auto bytes = [&](int g) { return size_t(4 * g * nk + g + 1) * SR::SW * sizeof(uint32_t); };
-		while (bytes(G) > 110 * 1024 && G > 1) --G;   // two CTAs per SM
-		size_t smem = bytes(G);
-		if (smem > 48 * 1024)
-		{
-			cudaError_t e = cudaFuncSetAttribute(k_deriv<QB_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-			if (e != cudaSuccess) return e;
-		}
-		int blocks = (n_tables + G - 1) / G;
-		k_deriv<QB_L><<<blocks, G * nk, smem, st>>>(cx, n_tables, G, tref, delta, b, pw, fr);
-		return cudaSuccess;
+		int threads = 128;
+		int64_t total = int64_t(n_tables) * (cx.n_max + 1);
+		k_scale<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, tref, delta, b, pw, a);
+	}
+	template <>
+	void launch_horner<QB_L>(const DevCtx& cx, int n_tables, const mpf<QB_L>* a, const mpf<QB_L>* pw, mpf<QB_L>* fr,
+	                         cudaStream_t st)
+	{
+		int threads = 128;
+		int64_t total = int64_t(n_tables) * (int(cx.lambda) + 1);
+		k_horner<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, a, pw, fr);
 	}
 #elif QB_KGROUP == 3
 	template <>

@@ -3,8 +3,9 @@
 //   k_rec_coeffs   one thread per (series job, recurrence coefficient)        -> coef[job][40]
 //   k_polyvals     one thread per (series job, n): the recurrence polynomials at n  -> pv[job][n][8]
 //   k_series       one thread per series job, n_max sequential steps          -> b[job][0..n_max]
-//   k_deriv        one CTA per G tables, (lambda+1) Horner chains per table running as a software pipeline through
-//                  shared memory (chain k consumes the coefficient chain k-1 scaled one step earlier) -> fr[table][k]
+//   k_pow          one thread per (table, power): 4^Delta and rho^(Delta-k)              -> pw[table][lambda+2]
+//   k_scale        one thread per (table, n): the lambda+1 scaled coefficient arrays     -> a[table][k][n]
+//   k_horner       one thread per (table, k): Horner sum, times rho^q / k!               -> fr[table][k]
 //   k_finish       one thread per table: rho->z matrix and the transverse (Casimir) recursion        -> g[table][dim_M]
 //   k_vtod         one thread per distinct d: 4^-d and the v^d table
 //   k_fblock       one thread per (term, kept entry): 2 * proj(v^d * g)
@@ -136,107 +137,77 @@ namespace qb
 		copy(pw[size_t(t) * np + j], r);
 	}
 
-	// shared-memory record with an odd word stride (conflict-free when every thread walks its own record)
+	// rho-derivative stage, part 1: every scaled coefficient array a_k[n], k = 0..lambda (reference: h *= 4^Delta,
+	// src/hor_recursion.cpp:43, then lambda times RealFunctionWithPower::derivate, real_function.hpp:236-240):
+	//   a_0[n] = b[n] * 4^Delta,   a_k[n] = a_{k-1}[n] * (q_{k-1} + n),   q_k = q_{k-1} - 1,  q_0 = Delta
+	// One thread per (table, n) walks k: no dependency between threads, no barrier.  Layout a[table][k][n] (n fastest) so
+	// that part 2 streams each chain contiguously.  The arrays (lambda+1 times the series, ~1.1 MB per table at the
+	// north-star size) live in HBM: written once here, read once by k_horner.
 	template <int L>
-	struct SRec
+	__global__ void __launch_bounds__(128, 4)
+	    k_scale(DevCtx cx, int n_tables, const TableRef* __restrict__ tref, const mpf<L>* __restrict__ delta,
+	            const mpf<L>* __restrict__ b, const mpf<L>* __restrict__ pw, mpf<L>* __restrict__ a)
 	{
-		static constexpr int W = L + 2;
-		static constexpr int SW = (W % 2 == 0) ? W + 1 : W;
-		static __device__ __forceinline__ mpf<L>& at(uint32_t* base, int idx) { return *reinterpret_cast<mpf<L>*>(base + size_t(idx) * SW); }
-	};
-
-	// Shared-memory pipeline of the lambda+1 derivative chains.  One CTA = G tables x (lambda+1) threads; thread (g, k) owns
-	// chain k of table g.  At step tau it takes coefficient a_{k-1}[n] (n = n_max - tau + k) that chain k-1 produced one
-	// step earlier (double-buffered in shared memory), scales it to a_k[n] = a_{k-1}[n] * (q_{k-1} + n), and feeds its Horner
-	// sum s_k <- s_k * rho + a_k[n].  All per-thread state (Horner sum, q_{k-1}) lives in shared memory; the limb arithmetic
-	// itself runs in registers (fastops.cuh), so the stack is touched only on the rare generic fallbacks.
-	template <int L>
-	__global__ void __launch_bounds__(192, 2)
-	    k_deriv(DevCtx cx, int n_tables, int G, const TableRef* __restrict__ tref, const mpf<L>* __restrict__ delta,
-	            const mpf<L>* __restrict__ b, const mpf<L>* __restrict__ pw, mpf<L>* __restrict__ fr)
-	{
-		extern __shared__ uint32_t smem_raw[];
-		using SR = SRec<L>;
+		const uint32_t n1 = cx.n_max + 1;
+		const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+		const int t = int(gid / n1);
+		const uint32_t n = uint32_t(gid % n1);
+		if (t >= n_tables) return;
 		const int nk = int(cx.lambda) + 1;
-		const int T = G * nk;
-		const int tid = threadIdx.x;
-		const int g = tid / nk, k = tid % nk;
-		const int t = blockIdx.x * G + g;
-		const bool active = (g < G) && (t < n_tables);
-		uint32_t* buf0 = smem_raw;
-		uint32_t* buf1 = buf0 + size_t(T) * SR::SW;
-		uint32_t* accS = buf1 + size_t(T) * SR::SW;   // Horner sums
-		uint32_t* accQ = accS + size_t(T) * SR::SW;   // q_{k-1}
-		uint32_t* c4s = accQ + size_t(T) * SR::SW;    // 4^Delta per table
-		uint32_t* rhos = c4s + size_t(G) * SR::SW;    // rho
 		const int prec = cx.prec;
-		const uint32_t n_max = cx.n_max;
-		const mpf<L>* b0p = nullptr;
-		const mpf<L>* b1p = nullptr;
-		if (tid == 0) copy(SR::at(rhos, 0), *reinterpret_cast<const mpf<L>*>(cx.rho));
-		if (active)
+		const TableRef tr = tref[t];
+		mpf<L>* at = a + size_t(t) * nk * n1 + n;
+		mpf<L> cur, q;
 		{
-			// q_{k-1} = Delta - (k-1) by rounded decrements                 (real_function.hpp:239 `pow_ -= 1`)
-			mpf<L> q;
-			copy(q, delta[t]);
-			for (int j = 0; j + 1 < k; ++j) add_si(q, q, -1, prec);
-			copy(SR::at(accQ, tid), q);
-			set_zero(SR::at(accS, tid));
-			if (k == 0) copy(SR::at(c4s, g), pw[size_t(t) * (nk + 1)]);
-			TableRef tr = tref[t];
-			b0p = b + size_t(tr.job0) * (n_max + 1);
-			b1p = tr.job1 >= 0 ? b + size_t(tr.job1) * (n_max + 1) : nullptr;
-		}
-		__syncthreads();
-		const mpf<L>& rho = SR::at(rhos, 0);
-		mpf<L>& s = SR::at(accS, tid);
-		const int steps = int(n_max) + nk;
-		for (int tau = 0; tau < steps; ++tau)
-		{
-			uint32_t* cur = (tau & 1) ? buf1 : buf0;
-			uint32_t* prv = (tau & 1) ? buf0 : buf1;
-			int idx = tau - k;  // 0 .. n_max  <->  n = n_max - idx
-			if (active && idx >= 0 && idx <= int(n_max))
+			const mpf<L>& c4 = pw[size_t(t) * (nk + 1)];
+			if (tr.job1 >= 0)
 			{
-				uint32_t n = n_max - uint32_t(idx);
-				mpf<L>& a = SR::at(cur, tid);
-				if (k == 0)
-				{
-					if (b1p)
-					{
-						// divergent operator: average of the two shifted series           (hor_recursion.cpp:23-27)
-						mpf<L> u, v;
-						copy(u, b0p[n]);
-						copy(v, b1p[n]);
-						add(u, u, v, prec);
-						mul_2si(u, u, -1);
-						fast::mul(a, u, SR::at(c4s, g), prec);
-					}
-					else
-						fast::mul(a, b0p[n], SR::at(c4s, g), prec);                  // h *= 4^Delta (hor_recursion.cpp:43)
-				}
-				else
-				{
-					mpf<L> f;
-					fast::add_small(f, SR::at(accQ, tid), int64_t(n), prec);         // q_{k-1} + n
-					fast::mul(a, SR::at(prv, tid - 1), f, prec);                     // derivate (real_function.hpp:236-240)
-				}
-				if (idx == 0)
-					copy(s, a);
-				else
-					fast::fma(s, s, rho, a, prec);                                   // Horner (real_function.hpp:248-259)
+				// divergent operator: average of the two shifted series               (hor_recursion.cpp:23-27)
+				mpf<L> u, v;
+				copy(u, b[size_t(tr.job0) * n1 + n]);
+				copy(v, b[size_t(tr.job1) * n1 + n]);
+				add(u, u, v, prec);
+				mul_2si(u, u, -1);
+				fast::mul(cur, u, c4, prec);
 			}
-			__syncthreads();
+			else
+				fast::mul(cur, b[size_t(tr.job0) * n1 + n], c4, prec);
 		}
-		if (active)
+		copy(at[0], cur);
+		copy(q, delta[t]);
+		for (int k = 1; k < nk; ++k)
 		{
-			mpf<L> sl, rp, kf, f;
-			copy(sl, s);
-			copy(rp, pw[size_t(t) * (nk + 1) + 1 + k]);
-			copy(kf, reinterpret_cast<const mpf<L>*>(cx.kfact)[k]);
-			deriv_finish(f, sl, rp, kf, uint32_t(k), prec);
-			copy(fr[size_t(t) * nk + k], f);
+			mpf<L> f, nxt;
+			fast::add_small(f, q, int64_t(n), prec);   // q_{k-1} + n
+			fast::mul(nxt, cur, f, prec);
+			copy(at[size_t(k) * n1], nxt);
+			copy(cur, nxt);
+			fast::add_small(q, q, -1, prec);           // pow_ -= 1 (real_function.hpp:239)
 		}
+	}
+
+	// rho-derivative stage, part 2: Horner sums s_k = sum_n a_k[n] rho^n (approximate, real_function.hpp:248-259) and
+	// f_k = s_k * rho^(q_k) / k! (real_function.hpp:262, hor_recursion.cpp:46-53).  One thread per (table, k).
+	template <int L>
+	__global__ void __launch_bounds__(128, 4)
+	    k_horner(DevCtx cx, int n_tables, const mpf<L>* __restrict__ a, const mpf<L>* __restrict__ pw, mpf<L>* __restrict__ fr)
+	{
+		const int nk = int(cx.lambda) + 1;
+		const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+		const int t = int(gid / nk), k = int(gid % nk);
+		if (t >= n_tables) return;
+		const uint32_t n1 = cx.n_max + 1;
+		const int prec = cx.prec;
+		const mpf<L>* ak = a + (size_t(t) * nk + k) * n1;
+		mpf<L> rho, s;
+		copy(rho, *reinterpret_cast<const mpf<L>*>(cx.rho));
+		copy(s, ak[cx.n_max]);
+		for (uint32_t n = cx.n_max; n-- > 0;) fast::fma(s, s, rho, ak[n], prec);
+		mpf<L> rp, kf, f;
+		copy(rp, pw[size_t(t) * (nk + 1) + 1 + k]);
+		copy(kf, reinterpret_cast<const mpf<L>*>(cx.kfact)[k]);
+		deriv_finish(f, s, rp, kf, uint32_t(k), prec);
+		copy(fr[size_t(t) * nk + k], f);
 	}
 
 	template <int L>
