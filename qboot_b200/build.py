@@ -3,7 +3,7 @@
 Translation units: per limb count L one host-side engine (engine_inst.cu, -DQB_L) and five kernel groups
 (kernel_inst.cu, -DQB_L -DQB_KGROUP=0..4), plus the C ABI (capi.cu).  All device arithmetic is force-inlined into the
 kernels (see mpf.cuh), so the kernel groups are the expensive part; they compile in parallel and are cached per object
-by a digest of the sources.  No JIT cache, no torch extension machinery: the .so sits next to this file so that it
+by a digest of its own preprocessed source.  No JIT cache, no torch extension machinery: the .so sits next to this file so that it
 travels with the repository snapshot to the GPU box.
 """
 from __future__ import annotations
@@ -29,16 +29,15 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
-def _sources_digest() -> str:
+def _tu_digest(cmd) -> str:
+    """digest of ONE translation unit: its preprocessed source (so only the headers it includes matter) + the flags"""
+    i = cmd.index("-c")
+    pre = subprocess.run([cmd[0], *[a for a in cmd[1:i] if a not in ("-lineinfo",)], "-E", cmd[i + 1]],
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
     h = hashlib.sha256()
-    for d, _, files in sorted(os.walk(CSRC)):
-        for f in sorted(files):
-            with open(os.path.join(d, f), "rb") as fh:
-                h.update(f.encode())
-                h.update(fh.read())
-    with open(os.path.join(ROOT, "include", "qboot_b200.h"), "rb") as fh:
-        h.update(fh.read())
-    h.update(" ".join(COMMON + ARCH).encode())
+    # drop line markers: they carry absolute paths
+    h.update(b"\n".join(l for l in pre.stdout.split(b"\n") if not l.startswith(b"#")))
+    h.update(" ".join(cmd[:i]).encode())
     return h.hexdigest()
 
 
@@ -55,7 +54,6 @@ def _run(cmd, log, stamp=None, digest=None):
 
 def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(BUILD, exist_ok=True)
-    digest = _sources_digest()
     jobs = []  # (cmd, log, obj)
 
     def add(name, src, defs):
@@ -70,10 +68,10 @@ def build(force: bool = False, verbose: bool = True) -> str:
     add("capi", "capi.cu", ["-DQB_L_LIST=" + " ".join(f"X({L})" for L in LIMBS)])
 
     todo = []
-    for cmd, log, obj in jobs:
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        keys = list(ex.map(lambda j: _tu_digest(j[0]), jobs))
+    for (cmd, log, obj), key in zip(jobs, keys):
         stamp = obj + ".stamp"
-        key = digest + " " + " ".join(cmd)
-        key = hashlib.sha256(key.encode()).hexdigest()
         if force or not (os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == key):
             todo.append((cmd, log, stamp, key))
     if todo or not os.path.exists(LIB):

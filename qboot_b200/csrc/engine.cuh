@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -101,7 +102,14 @@ namespace qb
 		uint32_t* t_spin = nullptr;
 		T *j_delta = nullptr, *j_S = nullptr, *j_P = nullptr, *j_b0 = nullptr;
 		uint32_t* j_spin = nullptr;
-		cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+		std::vector<cudaEvent_t> ev;    // 5 per chunk when timing
+		static constexpr int NSTREAMS = 3;
+		cudaStream_t streams[NSTREAMS] = {nullptr, nullptr, nullptr};
+		cudaEvent_t join_ev[NSTREAMS] = {nullptr, nullptr, nullptr}, fork_ev = nullptr;
+		std::vector<int> job_of_table;  // first job of every table (+ sentinel)
+		std::vector<int> chunk_t;       // table boundaries of the chunks
+		int n_chunks = 1, timed_chunks = 0;
+		size_t a_slot_records = 0;      // records of one stream's slice of the scaled-coefficient scratch
 
 		Engine(int dev, int prec_bits)
 		{
@@ -115,6 +123,8 @@ namespace qb
 			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_pv, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
 			                  &d_fb_terms})
 				b->release();
+			for (int i = 1; i < NSTREAMS; ++i)
+				if (streams[i]) cudaStreamDestroy(streams[i]);
 			if (stream) cudaStreamDestroy(stream);
 		}
 		// QB_DEBUG_SYNC=1: synchronise after every kernel so that a fault is attributed to the kernel that raised it
@@ -151,7 +161,7 @@ namespace qb
 			b0_cache.clear();
 			// upload: rho | mat | kfact | ln2e | ln4e | lnrhoe
 			size_t n1 = size_t(lam) + 1;
-			size_t bytes = sizeof(T) * (1 + n1 * n1 + n1) + 3 * sizeof(mpf<E>);
+			size_t bytes = sizeof(T) * (1 + n1 * n1 + n1) + (3 + n1) * sizeof(mpf<E>);
 			if (d_consts.ensure(bytes)) return -7;
 			std::vector<uint8_t> host(bytes);
 			uint8_t* p = host.data();
@@ -165,6 +175,7 @@ namespace qb
 			put(&consts.ln2e, sizeof(mpf<E>));
 			put(&consts.ln4e, sizeof(mpf<E>));
 			put(&consts.lnrhoe, sizeof(mpf<E>));
+			put(consts.rhoinv.data(), sizeof(mpf<E>) * n1);
 			QB_CU(cudaMemcpyAsync(d_consts.p, host.data(), bytes, cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaStreamSynchronize(stream));
 			const uint8_t* d = d_consts.as<uint8_t>();
@@ -179,6 +190,7 @@ namespace qb
 			cx.ln2e = reinterpret_cast<const uint32_t*>(de);
 			cx.ln4e = reinterpret_cast<const uint32_t*>(de + sizeof(mpf<E>));
 			cx.lnrhoe = reinterpret_cast<const uint32_t*>(de + 2 * sizeof(mpf<E>));
+			cx.rhoinv = reinterpret_cast<const uint32_t*>(de + 3 * sizeof(mpf<E>));
 			has_ctx = true;
 			return 0;
 		}
@@ -295,11 +307,21 @@ namespace qb
 			}
 			n_tables = n;
 			n_jobs = int(jd.size());
+			job_of_table.assign(size_t(n) + 1, n_jobs);
+			for (int t = 0; t < n; ++t) job_of_table[size_t(t)] = tr[size_t(t)].job0;
+			// chunks of ~CHUNK tables; the scaled-coefficient scratch is one slot per stream
+			static const int CHUNK = std::getenv("QB_CHUNK") ? std::max(256, std::atoi(std::getenv("QB_CHUNK"))) : 6144;
+			n_chunks = n > CHUNK ? (n + CHUNK - 1) / CHUNK : 1;
+			chunk_t.assign(size_t(n_chunks) + 1, n);
+			for (int c = 0; c < n_chunks; ++c) chunk_t[size_t(c)] = int(int64_t(n) * c / n_chunks);
+			int max_chunk = 0;
+			for (int c = 0; c < n_chunks; ++c) max_chunk = std::max(max_chunk, chunk_t[size_t(c) + 1] - chunk_t[size_t(c)]);
+			a_slot_records = (size_t(lambda) + 1) * (size_t(n_max) + 1) * size_t(n_chunks > 1 ? max_chunk : n);
 			if (n == 0) return 0;
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
-			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * n1 * (size_t(n_max) + 1) * nt) ||
+			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * a_slot_records * size_t(n_chunks > 1 ? NSTREAMS : 1)) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;
 			t_delta = d_in.as<T>();
@@ -325,44 +347,96 @@ namespace qb
 			return 0;
 		}
 
+		// all kernels of the table range [t0, t1) (jobs [j0, j1)) on stream st
+		int run_range(int t0, int t1, int j0, int j1, cudaStream_t st, cudaEvent_t* ev)
+		{
+			const bool timed = ev != nullptr;
+			const int nt = t1 - t0, nj = j1 - j0;
+			const size_t n1 = size_t(n_max) + 1, nk = size_t(lambda) + 1, dimM = size_t(cf_dim(int(lambda)));
+			T* coef = d_coef.as<T>() + size_t(j0) * QB_NCOEF;
+			T* pv = d_pv.as<T>() + size_t(j0) * n_max * 8;
+			if (timed) QB_CU(cudaEventRecord(ev[0], st));
+			launch_rec_coeffs<L>(cx, nj, j_delta + j0, j_spin + j0, j_S + j0, j_P + j0, coef, st);
+			++launches;
+			if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
+			if (timed) QB_CU(cudaEventRecord(ev[1], st));
+			launch_polyvals<L>(cx, nj, j_spin + j0, coef, pv, st);
+			++launches;
+			launch_series<L>(cx, nj, j_delta + j0, j_spin + j0, j_b0 + j0, pv, d_b.as<T>() + size_t(j0) * n1, st);
+			++launches;
+			if (int rc_ = debug_sync("k_series")) return rc_;
+			if (timed) QB_CU(cudaEventRecord(ev[2], st));
+			T* pw = d_pw.as<T>() + size_t(t0) * (nk + 1);
+			T* aa = d_a.as<T>();  // scratch of this stream's slot (see gblock_run)
+			launch_pow<L>(cx, nt, t_delta + t0, pw, st);
+			++launches;
+			// TableRef holds absolute job indices: hand the whole series array
+			launch_scale<L>(cx, nt, d_tref.as<TableRef>() + t0, t_delta + t0, d_b.as<T>(), pw, aa + size_t(a_slot_of(st)) * a_slot_records, st);
+			++launches;
+			launch_horner<L>(cx, nt, aa + size_t(a_slot_of(st)) * a_slot_records, pw, d_fr.as<T>() + size_t(t0) * nk, st);
+			++launches;
+			if (int rc_ = debug_sync("k_scale/k_horner")) return rc_;
+			if (timed) QB_CU(cudaEventRecord(ev[3], st));
+			launch_finish<L>(cx, nt, t_delta + t0, t_spin + t0, t_S + t0, t_P + t0, d_fr.as<T>() + size_t(t0) * nk,
+			                 d_g.as<T>() + size_t(t0) * dimM, st);
+			++launches;
+			if (int rc_ = debug_sync("k_finish")) return rc_;
+			if (timed) QB_CU(cudaEventRecord(ev[4], st));
+			return 0;
+		}
+		int a_slot_of(cudaStream_t st) const
+		{
+			for (int i = 0; i < NSTREAMS; ++i)
+				if (streams[i] == st) return i;
+			return 0;
+		}
+		// The batch is cut into chunks that round-robin over NSTREAMS streams: the series recurrence (one thread per job,
+		// latency-bound) of one chunk overlaps the throughput-bound scale / Horner kernels of another.  With timing
+		// enabled everything runs as one chunk on the handle's stream so that the per-kernel events are meaningful.
 		int gblock_run() override
 		{
 			if (!has_ctx) return -3;
 			if (n_tables == 0) return 0;
 			QB_CU(cudaSetDevice(device));
-			const int nk = int(lambda) + 1;
-			if (timing && !ev[0])
-				for (auto& e : ev) QB_CU(cudaEventCreate(&e));
-			if (timing) QB_CU(cudaEventRecord(ev[0], stream));
+			if (timing)
+				while (ev.size() < size_t(5) * size_t(n_chunks))
+				{
+					cudaEvent_t x;
+					QB_CU(cudaEventCreate(&x));
+					ev.push_back(x);
+				}
+			if (!streams[1])
 			{
-				launch_rec_coeffs<L>(cx, n_jobs, j_delta, j_spin, j_S, j_P, d_coef.as<T>(), stream);
-				++launches;
-				if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
-				if (timing) QB_CU(cudaEventRecord(ev[1], stream));
+				streams[0] = stream;
+				for (int i = 1; i < NSTREAMS; ++i) QB_CU(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+				for (int i = 0; i < NSTREAMS; ++i) QB_CU(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
+				QB_CU(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
 			}
+			if (timing || n_chunks == 1)
 			{
-				launch_polyvals<L>(cx, n_jobs, j_spin, d_coef.as<T>(), d_pv.as<T>(), stream);
-				++launches;
-				launch_series<L>(cx, n_jobs, j_delta, j_spin, j_b0, d_pv.as<T>(), d_b.as<T>(), stream);
-				++launches;
-				if (int rc_ = debug_sync("k_series")) return rc_;
-				if (timing) QB_CU(cudaEventRecord(ev[2], stream));
+				// one stream, chunk after chunk (same scratch slot), events around every kernel
+				timed_chunks = timing ? n_chunks : 0;
+				for (int c = 0; c < n_chunks; ++c)
+				{
+					const int t0 = chunk_t[size_t(c)], t1 = chunk_t[size_t(c) + 1];
+					if (int rc = run_range(t0, t1, job_of_table[size_t(t0)], job_of_table[size_t(t1)], stream,
+					                       timing ? ev.data() + 5 * c : nullptr))
+						return rc;
+				}
+				QB_CU(cudaGetLastError());
+				return 0;
 			}
+			QB_CU(cudaEventRecord(fork_ev, stream));
+			for (int i = 1; i < NSTREAMS; ++i) QB_CU(cudaStreamWaitEvent(streams[i], fork_ev, 0));
+			for (int c = 0; c < n_chunks; ++c)
 			{
-				launch_pow<L>(cx, n_tables, t_delta, d_pw.as<T>(), stream);
-				++launches;
-				launch_scale<L>(cx, n_tables, d_tref.as<TableRef>(), t_delta, d_b.as<T>(), d_pw.as<T>(), d_a.as<T>(), stream);
-				++launches;
-				launch_horner<L>(cx, n_tables, d_a.as<T>(), d_pw.as<T>(), d_fr.as<T>(), stream);
-				++launches;
-				if (int rc_ = debug_sync("k_deriv")) return rc_;
-				if (timing) QB_CU(cudaEventRecord(ev[3], stream));
+				const int t0 = chunk_t[size_t(c)], t1 = chunk_t[size_t(c) + 1];
+				if (int rc = run_range(t0, t1, job_of_table[size_t(t0)], job_of_table[size_t(t1)], streams[c % NSTREAMS], nullptr)) return rc;
 			}
+			for (int i = 1; i < NSTREAMS; ++i)
 			{
-				launch_finish<L>(cx, n_tables, t_delta, t_spin, t_S, t_P, d_fr.as<T>(), d_g.as<T>(), stream);
-				++launches;
-				if (int rc_ = debug_sync("k_finish")) return rc_;
-				if (timing) QB_CU(cudaEventRecord(ev[4], stream));
+				QB_CU(cudaEventRecord(join_ev[i], streams[i]));
+				QB_CU(cudaStreamWaitEvent(stream, join_ev[i], 0));
 			}
 			QB_CU(cudaGetLastError());
 			return 0;
@@ -370,12 +444,18 @@ namespace qb
 		// after a synchronise: read the per-kernel times of the last run
 		int collect_times()
 		{
-			if (!timing || !ev[0]) return 0;
-			for (int i = 0; i < 4; ++i)
-				if (cudaEventElapsedTime(&kernel_ms[i], ev[i], ev[i + 1]) != cudaSuccess)
+			for (float& x : kernel_ms) x = 0.f;
+			if (!timing) return 0;
+			for (int c = 0; c < timed_chunks; ++c)
+				for (int i = 0; i < 4; ++i)
 				{
-					cudaGetLastError();
-					kernel_ms[i] = 0.f;
+					float ms = 0.f;
+					if (cudaEventElapsedTime(&ms, ev[size_t(5 * c + i)], ev[size_t(5 * c + i + 1)]) != cudaSuccess)
+					{
+						cudaGetLastError();
+						ms = 0.f;
+					}
+					kernel_ms[i] += ms;
 				}
 			return 0;
 		}

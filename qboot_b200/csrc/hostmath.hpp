@@ -239,6 +239,7 @@ namespace qb
 		std::vector<mpf<L>> mat;    // (lambda+1)^2 row-major: rho-Taylor -> z-Taylor
 		std::vector<mpf<L>> kfact;  // k!
 		mpf<E> ln2e, ln4e, lnrhoe;
+		std::vector<mpf<E>> rhoinv;  // rho^-k at the extended width
 	};
 
 	namespace detail
@@ -367,5 +368,13 @@ namespace qb
 		mpf<E> rw;
 		widen(rw, c.rho);
 		log_ext(c.lnrhoe, rw, c.ln2e);
+		// rho^-k = exp(-k ln rho), each from its own exponential (no error accumulation)
+		c.rhoinv.resize(size_t(n1));
+		for (int k = 0; k <= lam; ++k)
+		{
+			mpf<E> tk;
+			mul_si(tk, c.lnrhoe, -int64_t(k), 32 * E);
+			exp_ext(c.rhoinv[size_t(k)], tk, c.ln2e);
+		}
 	}
 }  // namespace qb

@@ -3,7 +3,18 @@
 #if !defined(QB_L) || !defined(QB_KGROUP)
 #error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..4>"
 #endif
-#include "kernels.cuh"
+#include <cstdlib>
+#if QB_KGROUP == 0
+#include "kernels_g0.cuh"
+#elif QB_KGROUP == 1
+#include "kernels_g1.cuh"
+#elif QB_KGROUP == 2
+#include "kernels_g2.cuh"
+#elif QB_KGROUP == 3
+#include "kernels_g3.cuh"
+#else
+#include "kernels_g4.cuh"
+#endif
 
 namespace qb
 {
@@ -38,13 +49,29 @@ namespace qb
 		k_series<QB_L><<<(n_jobs + threads - 1) / threads, threads, 0, st>>>(cx, n_jobs, delta, spin, b0, pv, b);
 	}
 #elif QB_KGROUP == 2
+	template <class K>
+	static size_t co_residency_pad(K kernel)
+	{
+		if (std::getenv("QB_NO_PAD")) return 0;
+		const size_t bytes = 72 * 1024;
+		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) != cudaSuccess)
+		{
+			cudaGetLastError();
+			return 0;
+		}
+		return bytes;
+	}
 	template <>
 	void launch_scale<QB_L>(const DevCtx& cx, int n_tables, const TableRef* tref, const mpf<QB_L>* delta, const mpf<QB_L>* b,
 	                        const mpf<QB_L>* pw, mpf<QB_L>* a, cudaStream_t st)
 	{
 		int threads = 128;
 		int64_t total = int64_t(n_tables) * (cx.n_max + 1);
-		k_scale<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, tref, delta, b, pw, a);
+		// Unused dynamic shared memory caps the kernel at 3 CTAs per SM: the fourth would take the last registers, and the
+		// latency-bound one-thread-per-table kernels of the neighbouring streams (k_series, k_pow, k_finish) could not
+		// co-reside.  Costs nothing: the kernel is far from occupancy-bound.
+		static const size_t pad = co_residency_pad(k_scale<QB_L>);
+		k_scale<QB_L><<<unsigned((total + threads - 1) / threads), threads, pad, st>>>(cx, n_tables, tref, delta, b, pw, a);
 	}
 	template <>
 	void launch_horner<QB_L>(const DevCtx& cx, int n_tables, const mpf<QB_L>* a, const mpf<QB_L>* pw, mpf<QB_L>* fr,
@@ -52,7 +79,8 @@ namespace qb
 	{
 		int threads = 128;
 		int64_t total = int64_t(n_tables) * (int(cx.lambda) + 1);
-		k_horner<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, a, pw, fr);
+		static const size_t pad = co_residency_pad(k_horner<QB_L>);
+		k_horner<QB_L><<<unsigned((total + threads - 1) / threads), threads, pad, st>>>(cx, n_tables, a, pw, fr);
 	}
 #elif QB_KGROUP == 3
 	template <>
@@ -66,9 +94,8 @@ namespace qb
 	template <>
 	void launch_pow<QB_L>(const DevCtx& cx, int n_tables, const mpf<QB_L>* delta, mpf<QB_L>* pw, cudaStream_t st)
 	{
-		int threads = 128;
-		int64_t total = int64_t(n_tables) * (int(cx.lambda) + 2);
-		k_pow<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, delta, pw);
+		int threads = 32;
+		k_pow<QB_L><<<(n_tables + threads - 1) / threads, threads, 0, st>>>(cx, n_tables, delta, pw);
 	}
 	template <>
 	void launch_vtod<QB_L>(const DevCtx& cx, int n_d, const mpf<QB_L>* d, mpf<QB_L>* v, cudaStream_t st)

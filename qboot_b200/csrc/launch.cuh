@@ -20,6 +20,7 @@ namespace qb
 		const uint32_t* ln4e;
 		const uint32_t* lnrhoe;
 		const uint32_t* kfact;    // k!, k = 0..lambda, mpf<L>
+		const uint32_t* rhoinv;   // rho^-k, k = 0..lambda, mpf<L + QB_EXT_LIMBS>
 	};
 
 	// a series job: one run of the recurrence at (Delta', spin, S, P)

@@ -174,3 +174,17 @@ def test_error_behaviour():
     with pytest.raises(qb.QbError):
         qb.Engine(4096)  # no kernels for this precision
     eng.close()
+
+
+@pytest.mark.parametrize("prec", [512, 600, 800, 1024, 1200, 1536])
+def test_device_fast_paths_vs_mpfr(ref, prec):
+    """the register-resident routines with their PTX carry chains (fastops.cuh), on the device, against MPFR"""
+    from tests.test_host_arith import FAST, fast_cases
+
+    eng = _engine(prec, 20, 5)
+    for name, kw in fast_cases(ref, prec, 400, prec + 1):
+        want = ref.op(name, prec, **kw)
+        got = eng.op(FAST[name], **kw)
+        bad = [i for i in range(len(want)) if not np.array_equal(want[i], got[i])]
+        assert not bad, (name, bad[:5])
+    eng.close()

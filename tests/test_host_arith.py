@@ -144,3 +144,61 @@ def test_table_stages_vs_golden(hostemu, ref, name):
             fo = np.zeros_like(want)
             cnt = hostemu.qbh_fblock(prec, lam, P(g["fb_d"][sym].copy()), P(tab), sym, P(ce), P(fo))
             assert cnt == len(want) and np.array_equal(fo, want), ("fblock", t, sym)
+
+
+# ---- register-resident fast paths (fastops.cuh): host build with the carry chains emulated ----------------------------------
+FAST = dict(mul=40, fma=41, add=42, sub=43, mul_si=44, add_si=45, div=46)
+
+
+def _fast(emu, code, prec, a=None, b=None, c=None, ia=None):
+    W = words(prec)
+    arrs = [None if x is None else np.ascontiguousarray(x, dtype=np.uint32).reshape(-1, W) for x in (a, b, c)]
+    ints = None if ia is None else np.ascontiguousarray(ia, dtype=np.int64)
+    n = len(arrs[0])
+    out = np.zeros((n, W), dtype=np.uint32)
+    assert emu.qbh_op(prec, code, n, P(arrs[0]), P(arrs[1]), P(arrs[2]), P(ints), None, P(out), None) == 0
+    return out
+
+
+def fast_cases(ref, prec, n, seed):
+    """random operands plus the adversarial ones: c ~ -(a*b) with single-bit perturbations (cancellation of every depth) and
+    exponent gaps around 0, 32, 64, prec and beyond in both directions (rounding residues of the series are ~2^-prec)"""
+    from tests.golden.make_golden import rnd_num
+
+    rng = random.Random(seed)
+    L = (prec + 31) // 32
+    a = np.stack([rnd_num(rng, prec, -5, 5) for _ in range(n)])
+    b = np.stack([rnd_num(rng, prec, -5, 5) for _ in range(n)])
+    c = np.stack([rnd_num(rng, prec, -80, 80) for _ in range(n)])
+    prod = ref.op("mul", prec, a=a, b=b)
+    gaps = [0, 0, 1, -1, 31, 32, 33, 63, 64, 65, -31, -32, -33, -64, -65, prec - 33, prec, prec + 1, prec + 33, prec + 64, prec + 65, 3000,
+            -prec, -prec - 1, -prec - 65, -3000]
+    for i in range(0, n, 2):
+        c[i] = prod[i].copy()
+        if (c[i, 0] & 3) == 1:
+            c[i, 0] ^= 0x80000000
+            if rng.random() < 0.8:
+                li = rng.randrange(L)
+                c[i, 2 + li] ^= 1 << rng.randrange(31 if li == L - 1 else 32)
+            c[i, 2] &= (0xFFFFFFFF << ((-prec) % 32)) & 0xFFFFFFFF
+            c[i, 1] = np.uint32((int(np.int32(c[i, 1])) + rng.choice(gaps + [rng.randint(-prec - 80, prec + 80)])) & 0xFFFFFFFF)
+    ia = np.array([rng.choice([1, -1, 2, 3, 7, 400, -12345, 2**31 - 1, 2**32 - 1, -(2**32 - 1)]) for _ in range(n)], dtype=np.int64)
+    b2 = b.copy()
+    for i in range(0, n, 3):
+        b2[i] = a[i]
+        li = rng.randrange(L)
+        b2[i, 2 + li] ^= 1 << rng.randrange(31 if li == L - 1 else 32)
+        b2[i, 2] &= (0xFFFFFFFF << ((-prec) % 32)) & 0xFFFFFFFF
+    ok = [i for i in range(n) if (b2[i, 0] & 3) == 1 and (b[i, 0] & 3) == 1]
+    return [("mul", dict(a=a, b=b)), ("fma", dict(a=a, b=b, c=c)), ("add", dict(a=prod, b=c)), ("sub", dict(a=prod, b=c)),
+            ("add", dict(a=a, b=b)), ("mul_si", dict(a=a, ia=ia)), ("add_si", dict(a=a, ia=ia)), ("add_si", dict(a=c, ia=ia)),
+            ("div", dict(a=a[ok], b=b[ok])), ("div", dict(a=a[ok], b=b2[ok]))]
+
+
+@pytest.mark.parametrize("prec", [64, 96, 100, 128, 600, 800, 1000, 1024, 1200, 1536])
+def test_fast_paths_vs_mpfr(hostemu, ref, prec):
+    for name, kw in fast_cases(ref, prec, 400, prec):
+        want = ref.op(name, prec, **kw)
+        got = _fast(hostemu, FAST[name], prec, **kw)
+        bad = [i for i in range(len(want)) if not np.array_equal(want[i], got[i])]
+        assert not bad, (name, bad[:5])
