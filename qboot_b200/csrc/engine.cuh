@@ -103,13 +103,15 @@ namespace qb
 		T *j_delta = nullptr, *j_S = nullptr, *j_P = nullptr, *j_b0 = nullptr;
 		uint32_t* j_spin = nullptr;
 		std::vector<cudaEvent_t> ev;    // 5 per chunk when timing
-		static constexpr int NSTREAMS = 3;
-		cudaStream_t streams[NSTREAMS] = {nullptr, nullptr, nullptr};
-		cudaEvent_t join_ev[NSTREAMS] = {nullptr, nullptr, nullptr}, fork_ev = nullptr;
+		cudaStream_t lo_stream = nullptr;        // wide kernels of all chunks
+		std::vector<cudaStream_t> hi_streams;    // latency-bound kernels, one stream per chunk
+		std::vector<cudaEvent_t> dep_ev;         // 4 per chunk
+		cudaEvent_t fork_ev = nullptr;
+		int hi_priority = 0;
 		std::vector<int> job_of_table;  // first job of every table (+ sentinel)
 		std::vector<int> chunk_t;       // table boundaries of the chunks
 		int n_chunks = 1, timed_chunks = 0;
-		size_t a_slot_records = 0;      // records of one stream's slice of the scaled-coefficient scratch
+		size_t a_slot_records = 0;      // records of the scaled-coefficient scratch (largest chunk)
 
 		Engine(int dev, int prec_bits)
 		{
@@ -123,8 +125,8 @@ namespace qb
 			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_pv, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
 			                  &d_fb_terms})
 				b->release();
-			for (int i = 1; i < NSTREAMS; ++i)
-				if (streams[i]) cudaStreamDestroy(streams[i]);
+			for (cudaStream_t s : hi_streams) cudaStreamDestroy(s);
+			if (lo_stream) cudaStreamDestroy(lo_stream);
 			if (stream) cudaStreamDestroy(stream);
 		}
 		// QB_DEBUG_SYNC=1: synchronise after every kernel so that a fault is attributed to the kernel that raised it
@@ -311,7 +313,8 @@ namespace qb
 			for (int t = 0; t < n; ++t) job_of_table[size_t(t)] = tr[size_t(t)].job0;
 			// chunks of ~CHUNK tables; the scaled-coefficient scratch is one slot per stream
 			static const int CHUNK = std::getenv("QB_CHUNK") ? std::max(256, std::atoi(std::getenv("QB_CHUNK"))) : 6144;
-			n_chunks = n > CHUNK ? (n + CHUNK - 1) / CHUNK : 1;
+			// at most 16 chunks (streams); larger batches get larger chunks
+			n_chunks = n > CHUNK ? std::min(16, (n + CHUNK - 1) / CHUNK) : 1;
 			chunk_t.assign(size_t(n_chunks) + 1, n);
 			for (int c = 0; c < n_chunks; ++c) chunk_t[size_t(c)] = int(int64_t(n) * c / n_chunks);
 			int max_chunk = 0;
@@ -321,7 +324,7 @@ namespace qb
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
-			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * a_slot_records * size_t(n_chunks > 1 ? NSTREAMS : 1)) ||
+			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * a_slot_records) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;
 			t_delta = d_in.as<T>();
@@ -347,52 +350,84 @@ namespace qb
 			return 0;
 		}
 
-		// all kernels of the table range [t0, t1) (jobs [j0, j1)) on stream st
-		int run_range(int t0, int t1, int j0, int j1, cudaStream_t st, cudaEvent_t* ev)
+		// ---- the stages of one chunk (tables [t0, t1), jobs [j0, j1)) ---------------------------------------------------
+		struct Range
 		{
-			const bool timed = ev != nullptr;
-			const int nt = t1 - t0, nj = j1 - j0;
-			const size_t n1 = size_t(n_max) + 1, nk = size_t(lambda) + 1, dimM = size_t(cf_dim(int(lambda)));
-			T* coef = d_coef.as<T>() + size_t(j0) * QB_NCOEF;
-			T* pv = d_pv.as<T>() + size_t(j0) * n_max * 8;
-			if (timed) QB_CU(cudaEventRecord(ev[0], st));
-			launch_rec_coeffs<L>(cx, nj, j_delta + j0, j_spin + j0, j_S + j0, j_P + j0, coef, st);
+			int t0, t1, j0, j1;
+		};
+		Range range_of(int c) const
+		{
+			const int t0 = chunk_t[size_t(c)], t1 = chunk_t[size_t(c) + 1];
+			return Range{t0, t1, job_of_table[size_t(t0)], job_of_table[size_t(t1)]};
+		}
+		void stage_rec(const Range& r, cudaStream_t st)
+		{
+			launch_rec_coeffs<L>(cx, r.j1 - r.j0, j_delta + r.j0, j_spin + r.j0, j_S + r.j0, j_P + r.j0,
+			                     d_coef.as<T>() + size_t(r.j0) * QB_NCOEF, st);
 			++launches;
+		}
+		void stage_polyvals(const Range& r, cudaStream_t st)
+		{
+			launch_polyvals<L>(cx, r.j1 - r.j0, j_spin + r.j0, d_coef.as<T>() + size_t(r.j0) * QB_NCOEF,
+			                   d_pv.as<T>() + size_t(r.j0) * n_max * 8, st);
+			++launches;
+		}
+		void stage_series(const Range& r, cudaStream_t st)
+		{
+			launch_series<L>(cx, r.j1 - r.j0, j_delta + r.j0, j_spin + r.j0, j_b0 + r.j0, d_pv.as<T>() + size_t(r.j0) * n_max * 8,
+			                 d_b.as<T>() + size_t(r.j0) * (size_t(n_max) + 1), st);
+			++launches;
+		}
+		void stage_pow(const Range& r, cudaStream_t st)
+		{
+			launch_pow<L>(cx, r.t1 - r.t0, t_delta + r.t0, d_pw.as<T>() + size_t(r.t0) * (size_t(lambda) + 2), st);
+			++launches;
+		}
+		void stage_deriv(const Range& r, cudaStream_t st)
+		{
+			const size_t nk = size_t(lambda) + 1;
+			T* pw = d_pw.as<T>() + size_t(r.t0) * (nk + 1);
+			// TableRef holds absolute job indices: hand the whole series array.  One scratch slot: the (scale, horner)
+			// pairs of all chunks are serialised on one stream.
+			launch_scale<L>(cx, r.t1 - r.t0, d_tref.as<TableRef>() + r.t0, t_delta + r.t0, d_b.as<T>(), pw, d_a.as<T>(), st);
+			++launches;
+			launch_horner<L>(cx, r.t1 - r.t0, d_a.as<T>(), pw, d_fr.as<T>() + size_t(r.t0) * nk, st);
+			++launches;
+		}
+		void stage_finish(const Range& r, cudaStream_t st)
+		{
+			const size_t nk = size_t(lambda) + 1, dimM = size_t(cf_dim(int(lambda)));
+			launch_finish<L>(cx, r.t1 - r.t0, t_delta + r.t0, t_spin + r.t0, t_S + r.t0, t_P + r.t0,
+			                 d_fr.as<T>() + size_t(r.t0) * nk, d_g.as<T>() + size_t(r.t0) * dimM, st);
+			++launches;
+		}
+		// one chunk, all stages back to back on one stream, optionally with an event around every stage
+		int run_serial(int c, cudaStream_t st, cudaEvent_t* ev)
+		{
+			const Range r = range_of(c);
+			const bool timed = ev != nullptr;
+			if (timed) QB_CU(cudaEventRecord(ev[0], st));
+			stage_rec(r, st);
 			if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
 			if (timed) QB_CU(cudaEventRecord(ev[1], st));
-			launch_polyvals<L>(cx, nj, j_spin + j0, coef, pv, st);
-			++launches;
-			launch_series<L>(cx, nj, j_delta + j0, j_spin + j0, j_b0 + j0, pv, d_b.as<T>() + size_t(j0) * n1, st);
-			++launches;
-			if (int rc_ = debug_sync("k_series")) return rc_;
+			stage_polyvals(r, st);
+			stage_series(r, st);
+			if (int rc_ = debug_sync("k_polyvals/k_series")) return rc_;
 			if (timed) QB_CU(cudaEventRecord(ev[2], st));
-			T* pw = d_pw.as<T>() + size_t(t0) * (nk + 1);
-			T* aa = d_a.as<T>();  // scratch of this stream's slot (see gblock_run)
-			launch_pow<L>(cx, nt, t_delta + t0, pw, st);
-			++launches;
-			// TableRef holds absolute job indices: hand the whole series array
-			launch_scale<L>(cx, nt, d_tref.as<TableRef>() + t0, t_delta + t0, d_b.as<T>(), pw, aa + size_t(a_slot_of(st)) * a_slot_records, st);
-			++launches;
-			launch_horner<L>(cx, nt, aa + size_t(a_slot_of(st)) * a_slot_records, pw, d_fr.as<T>() + size_t(t0) * nk, st);
-			++launches;
-			if (int rc_ = debug_sync("k_scale/k_horner")) return rc_;
+			stage_pow(r, st);
+			stage_deriv(r, st);
+			if (int rc_ = debug_sync("k_pow/k_scale/k_horner")) return rc_;
 			if (timed) QB_CU(cudaEventRecord(ev[3], st));
-			launch_finish<L>(cx, nt, t_delta + t0, t_spin + t0, t_S + t0, t_P + t0, d_fr.as<T>() + size_t(t0) * nk,
-			                 d_g.as<T>() + size_t(t0) * dimM, st);
-			++launches;
+			stage_finish(r, st);
 			if (int rc_ = debug_sync("k_finish")) return rc_;
 			if (timed) QB_CU(cudaEventRecord(ev[4], st));
 			return 0;
 		}
-		int a_slot_of(cudaStream_t st) const
-		{
-			for (int i = 0; i < NSTREAMS; ++i)
-				if (streams[i] == st) return i;
-			return 0;
-		}
-		// The batch is cut into chunks that round-robin over NSTREAMS streams: the series recurrence (one thread per job,
-		// latency-bound) of one chunk overlaps the throughput-bound scale / Horner kernels of another.  With timing
-		// enabled everything runs as one chunk on the handle's stream so that the per-kernel events are meaningful.
+		// The batch is cut into chunks.  The wide, throughput-bound kernels (coefficients, polynomial values, scale, Horner)
+		// of all chunks are serialised on one low-priority stream; the one-thread-per-table, latency-bound kernels (powers,
+		// series recurrence, transverse recursion) of every chunk run on that chunk's own high-priority stream, so that
+		// they overlap each other and the wide kernels of the neighbouring chunks.  Events carry the dependencies.
+		// With timing enabled (or QB_DEBUG_SYNC) everything runs chunk after chunk on the handle's stream instead.
 		int gblock_run() override
 		{
 			if (!has_ctx) return -3;
@@ -405,38 +440,62 @@ namespace qb
 					QB_CU(cudaEventCreate(&x));
 					ev.push_back(x);
 				}
-			if (!streams[1])
+			static const bool serial_env = std::getenv("QB_DEBUG_SYNC") != nullptr || std::getenv("QB_SERIAL") != nullptr;
+			if (timing || n_chunks == 1 || serial_env)
 			{
-				streams[0] = stream;
-				for (int i = 1; i < NSTREAMS; ++i) QB_CU(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
-				for (int i = 0; i < NSTREAMS; ++i) QB_CU(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
-				QB_CU(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
-			}
-			if (timing || n_chunks == 1)
-			{
-				// one stream, chunk after chunk (same scratch slot), events around every kernel
 				timed_chunks = timing ? n_chunks : 0;
 				for (int c = 0; c < n_chunks; ++c)
-				{
-					const int t0 = chunk_t[size_t(c)], t1 = chunk_t[size_t(c) + 1];
-					if (int rc = run_range(t0, t1, job_of_table[size_t(t0)], job_of_table[size_t(t1)], stream,
-					                       timing ? ev.data() + 5 * c : nullptr))
-						return rc;
-				}
+					if (int rc = run_serial(c, stream, timing ? ev.data() + 5 * c : nullptr)) return rc;
 				QB_CU(cudaGetLastError());
 				return 0;
 			}
+			if (!lo_stream)
+			{
+				int pr_lo = 0, pr_hi = 0;
+				QB_CU(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+				QB_CU(cudaStreamCreateWithPriority(&lo_stream, cudaStreamNonBlocking, pr_lo));
+				QB_CU(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+				hi_priority = pr_hi;
+			}
+			while (int(hi_streams.size()) < n_chunks)
+			{
+				cudaStream_t s;
+				QB_CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi_priority));
+				hi_streams.push_back(s);
+				for (int i = 0; i < 4; ++i)
+				{
+					cudaEvent_t x;
+					QB_CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+					dep_ev.push_back(x);
+				}
+			}
+			auto EV = [&](int c, int i) { return dep_ev[size_t(4 * c + i)]; };  // 0 poly done, 1 series done, 2 horner done, 3 finish done
 			QB_CU(cudaEventRecord(fork_ev, stream));
-			for (int i = 1; i < NSTREAMS; ++i) QB_CU(cudaStreamWaitEvent(streams[i], fork_ev, 0));
+			QB_CU(cudaStreamWaitEvent(lo_stream, fork_ev, 0));
+			for (int c = 0; c < n_chunks; ++c) QB_CU(cudaStreamWaitEvent(hi_streams[size_t(c)], fork_ev, 0));
 			for (int c = 0; c < n_chunks; ++c)
 			{
-				const int t0 = chunk_t[size_t(c)], t1 = chunk_t[size_t(c) + 1];
-				if (int rc = run_range(t0, t1, job_of_table[size_t(t0)], job_of_table[size_t(t1)], streams[c % NSTREAMS], nullptr)) return rc;
+				const Range r = range_of(c);
+				stage_rec(r, lo_stream);
+				stage_polyvals(r, lo_stream);
+				QB_CU(cudaEventRecord(EV(c, 0), lo_stream));
+				cudaStream_t hs = hi_streams[size_t(c)];
+				stage_pow(r, hs);
+				QB_CU(cudaStreamWaitEvent(hs, EV(c, 0), 0));
+				stage_series(r, hs);
+				QB_CU(cudaEventRecord(EV(c, 1), hs));
 			}
-			for (int i = 1; i < NSTREAMS; ++i)
+			for (int c = 0; c < n_chunks; ++c)
 			{
-				QB_CU(cudaEventRecord(join_ev[i], streams[i]));
-				QB_CU(cudaStreamWaitEvent(stream, join_ev[i], 0));
+				const Range r = range_of(c);
+				cudaStream_t hs = hi_streams[size_t(c)];
+				QB_CU(cudaStreamWaitEvent(lo_stream, EV(c, 1), 0));
+				stage_deriv(r, lo_stream);
+				QB_CU(cudaEventRecord(EV(c, 2), lo_stream));
+				QB_CU(cudaStreamWaitEvent(hs, EV(c, 2), 0));
+				stage_finish(r, hs);
+				QB_CU(cudaEventRecord(EV(c, 3), hs));
+				QB_CU(cudaStreamWaitEvent(stream, EV(c, 3), 0));
 			}
 			QB_CU(cudaGetLastError());
 			return 0;
