@@ -124,6 +124,16 @@ def run_reference(args, rank, world):
     return 0
 
 
+def ncu_traffic(n_tables):
+    """DRAM bytes per launch of the dominant stage from the committed ncu --set full capture (profiles/), scaled from the
+    captured launch's table count to this run's chunk size; None when no capture is recorded."""
+    try:
+        rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+        return rec["deriv_dram_bytes_per_table"] * min(n_tables, rec.get("chunk_tables", n_tables))
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -263,9 +273,10 @@ def main():
         "kernel_ms_per_step": {"rec_coeffs": kms[0] / args.steps, "series": kms[1] / args.steps, "deriv": deriv_ms,
                                "finish": kms[3] / args.steps},
         "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlimb-MAC/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_deriv (rho-derivative chains)",
+                     "traffic": ncu_traffic(n), "kernel": "k_scale + k_horner (rho-derivative chains, stage a4)",
                      "whole_step_frac": total_work(spin) / (ms_per_step * 1e-3) / peak,
-                     "peak_source": "measured on this GPU by qb_imad_peak (dependency-free mad.wide.u32 chains, full occupancy)",
+                     "peak_source": "measured on this GPU by qb_imad_peak: dependency-free IMAD.WIDE.U32 chains at full occupancy "
+                                    "(32 x 32 + 64 -> 64; issues at 32 per clock per SM, half the 32-bit IMAD rate)",
                      "hbm_gbs_achieved": (out_bytes + n * (N_MAX + 1) * W * 4 * 2) / (ms_per_step * 1e-3) / 1e9},
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }

@@ -17,29 +17,34 @@ QB_L_LIST
 
 namespace qb
 {
-	// Integer multiply-add issue-rate probe: 8 independent mad.wide.u32 accumulation chains per thread, no memory
-	// traffic.  One "limb-MAC" (32 x 32 -> 64 multiply plus 64-bit accumulate) is the unit of the roofline.
+	// Limb-product issue-rate probe: 16 independent 32 x 32 + 64 -> 64 multiply-accumulate chains per thread
+	// (IMAD.WIDE.U32), no memory traffic.  One "limb-MAC" is the unit of the roofline.  The multiplier changes every
+	// iteration and differs per chain: with loop-invariant operands ptxas hoists the product and the loop degenerates
+	// into additions, which measures the wrong pipe (it did, in the first version of this probe).
 	static __global__ void k_imad_peak(uint64_t* out, int iters, uint32_t seed)
 	{
-		uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
-		uint64_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+		uint32_t a[16], y = seed * 2654435761u + blockIdx.x;
+		uint64_t c[16];
+#pragma unroll
+		for (int u = 0; u < 16; ++u)
+		{
+			a[u] = (seed + threadIdx.x) * uint32_t(2 * u + 3) + 1u;
+			c[u] = u + 1;
+		}
 #pragma unroll 1
 		for (int i = 0; i < iters; ++i)
 		{
 #pragma unroll
-			for (int u = 0; u < 8; ++u)
+			for (int r = 0; r < 4; ++r)
 			{
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c4) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c5) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c6) : "r"(a), "r"(b));
-				asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c7) : "r"(a), "r"(b));
+#pragma unroll
+				for (int u = 0; u < 16; ++u) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[u]) : "r"(a[u]), "r"(y));
+				y += 0x9e3779b9u;
 			}
 		}
-		uint64_t s = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+		uint64_t s = 0;
+#pragma unroll
+		for (int u = 0; u < 16; ++u) s ^= c[u];
 		if (s == 0x1234567ull) out[0] = s;  // keep the chains alive
 	}
 	void launch_imad_peak(uint64_t* out, int iters, uint32_t seed, int blocks, int threads, cudaStream_t st)

@@ -94,7 +94,7 @@ namespace qb
 		Rational eps{0, 1};
 		ContextConsts<L> consts;
 		std::map<uint32_t, T> b0_cache;
-		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_pv, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms;
+		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_qc, d_pv, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms;
 		DevCtx cx{};
 		int n_tables = 0, n_jobs = 0;
 		// layout of d_in: [delta | S | P] (tables) then spin; d_jobs: [delta | S | P | b0] (jobs) then spin
@@ -122,7 +122,7 @@ namespace qb
 		~Engine() override
 		{
 			cudaSetDevice(device);
-			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_pv, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
+			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_qc, &d_pv, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
 			                  &d_fb_terms})
 				b->release();
 			for (cudaStream_t s : hi_streams) cudaStreamDestroy(s);
@@ -324,7 +324,7 @@ namespace qb
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
-			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * a_slot_records) ||
+			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_qc.ensure(sizeof(T) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * a_slot_records) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;
 			t_delta = d_in.as<T>();
@@ -397,9 +397,8 @@ namespace qb
 		void stage_finish(const Range& r, cudaStream_t st)
 		{
 			const size_t nk = size_t(lambda) + 1, dimM = size_t(cf_dim(int(lambda)));
-			launch_finish<L>(cx, r.t1 - r.t0, t_delta + r.t0, t_spin + r.t0, t_S + r.t0, t_P + r.t0,
-			                 d_fr.as<T>() + size_t(r.t0) * nk, d_g.as<T>() + size_t(r.t0) * dimM, st);
-			++launches;
+			launches += launch_finish<L>(cx, r.t1 - r.t0, t_delta + r.t0, t_spin + r.t0, t_S + r.t0, t_P + r.t0,
+			                             d_fr.as<T>() + size_t(r.t0) * nk, d_g.as<T>() + size_t(r.t0) * dimM, d_qc.as<T>() + r.t0, st);
 		}
 		// one chunk, all stages back to back on one stream, optionally with an event around every stage
 		int run_serial(int c, cudaStream_t st, cudaEvent_t* ev)
@@ -488,15 +487,12 @@ namespace qb
 			for (int c = 0; c < n_chunks; ++c)
 			{
 				const Range r = range_of(c);
-				cudaStream_t hs = hi_streams[size_t(c)];
 				QB_CU(cudaStreamWaitEvent(lo_stream, EV(c, 1), 0));
 				stage_deriv(r, lo_stream);
-				QB_CU(cudaEventRecord(EV(c, 2), lo_stream));
-				QB_CU(cudaStreamWaitEvent(hs, EV(c, 2), 0));
-				stage_finish(r, hs);
-				QB_CU(cudaEventRecord(EV(c, 3), hs));
-				QB_CU(cudaStreamWaitEvent(stream, EV(c, 3), 0));
+				stage_finish(r, lo_stream);  // wide per-level kernels: same stream as the other wide stages
 			}
+			QB_CU(cudaEventRecord(EV(0, 3), lo_stream));
+			QB_CU(cudaStreamWaitEvent(stream, EV(0, 3), 0));
 			QB_CU(cudaGetLastError());
 			return 0;
 		}

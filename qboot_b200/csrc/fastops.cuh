@@ -131,11 +131,18 @@ namespace qb
 #pragma unroll
 			for (int j = 0; j < LP + 4; ++j) EV[j] = 0u;
 			uint32_t g0 = 0u, g1 = 0u, g2 = 0u, g3 = 0u, low = 0u;
+			// the two multiplier limbs of the NEXT row pair are fetched one iteration ahead: a may live in global or local
+			// memory and the rolled loop would otherwise expose that load's latency once per row pair
+			uint32_t n0 = a[0], n1 = (1 < L) ? a[1] : 0u;
 #pragma unroll 1
 			for (int i = 0; i < LP; i += 2)
 			{
-				const uint32_t a0 = a[i];
-				const uint32_t a1 = (i + 1 < L) ? a[i + 1] : 0u;
+				const uint32_t a0 = n0, a1 = n1;
+				if (i + 2 < LP)
+				{
+					n0 = a[i + 2];
+					n1 = (i + 3 < L) ? a[i + 3] : 0u;
+				}
 				QB_CY_DECL
 				// row i, even columns -> EV
 				QB_MAD_FIRST(EV[0], EV[1], a0, b[0]);

@@ -84,11 +84,20 @@ namespace qb
 	}
 #elif QB_KGROUP == 3
 	template <>
-	void launch_finish<QB_L>(const DevCtx& cx, int n_tables, const mpf<QB_L>* delta, const uint32_t* spin, const mpf<QB_L>* S,
-	                         const mpf<QB_L>* P, const mpf<QB_L>* fr, mpf<QB_L>* g, cudaStream_t st)
+	int launch_finish<QB_L>(const DevCtx& cx, int n_tables, const mpf<QB_L>* delta, const uint32_t* spin, const mpf<QB_L>* S,
+	                        const mpf<QB_L>* P, const mpf<QB_L>* fr, mpf<QB_L>* g, mpf<QB_L>* qc, cudaStream_t st)
 	{
-		int threads = 64;
-		k_finish<QB_L><<<(n_tables + threads - 1) / threads, threads, 0, st>>>(cx, n_tables, delta, spin, S, P, fr, g);
+		const int threads = 128, lambda = int(cx.lambda);
+		auto blocks = [&](int64_t total) { return unsigned((total + threads - 1) / threads); };
+		int count = 1;
+		k_rho_to_z<QB_L><<<blocks(int64_t(n_tables) * (lambda + 1)), threads, 0, st>>>(cx, n_tables, delta, spin, fr, g, qc);
+		for (int n = 1; n <= lambda / 2; ++n)
+		{
+			k_offdiag_val<QB_L><<<blocks(int64_t(n_tables) * (lambda - 2 * n + 1)), threads, 0, st>>>(cx, n_tables, n, S, P, qc, g);
+			k_offdiag_close<QB_L><<<blocks(n_tables), threads, 0, st>>>(cx, n_tables, n, g);
+			count += 2;
+		}
+		return count;
 	}
 #elif QB_KGROUP == 4
 	template <>

@@ -6,7 +6,7 @@
 //   kernels_g1.cuh  k_series      one thread per series job, n_max sequential steps                -> b[job][0..n_max]
 //   kernels_g2.cuh  k_scale       one thread per (table, n): the lambda+1 scaled coefficient arrays -> a[table][k][n]
 //                   k_horner      one thread per (table, k): Horner sum, times rho^q / k!           -> fr[table][k]
-//   kernels_g3.cuh  k_finish      one thread per table: rho->z matrix and the transverse recursion  -> g[table][dim_M]
+//   kernels_g3.cuh  k_rho_to_z, k_offdiag_val, k_offdiag_close: rho->z matrix and the transverse recursion, level by level -> g[table][dim_M]
 //   kernels_g4.cuh  k_pow         4^Delta and rho^(Delta-k);  k_vtod, k_fblock: v^d tables and F/H blocks
 // Numbers are records of L + 2 words (mpf<L>), arrays of records in HBM.  Arithmetic: mpf.cuh / fastops.cuh / hor.cuh /
 // block.cuh, all force-inlined (see mpf.cuh for why).
@@ -22,14 +22,15 @@
 namespace qb
 {
 	// recurrence coefficients a[i][d] of one job (_get_rec_coeffs, include/qboot/hor_formula.hpp:34-39): one thread per
-	// coefficient; the d == 0 threads of p_0 and p_{K-1} build those products of linear factors
+	// (coefficient, job) with the JOB as the fast index, so that the lanes of a warp walk the same monomial list and stay
+	// converged; the d == 0 threads of p_0 and p_{K-1} build those products of linear factors
 	template <int L>
 	__global__ void k_rec_coeffs(DevCtx cx, int n_jobs, const mpf<L>* __restrict__ delta, const uint32_t* __restrict__ spin,
 	                             const mpf<L>* __restrict__ S, const mpf<L>* __restrict__ P, mpf<L>* __restrict__ coef)
 	{
 		int gid = blockIdx.x * blockDim.x + threadIdx.x;
-		int job = gid / QB_NCOEF, c = gid % QB_NCOEF;
-		if (job >= n_jobs) return;
+		int c = gid / n_jobs, job = gid - c * n_jobs;
+		if (c >= QB_NCOEF) return;
 		uint32_t sp = spin[job];
 		const int K = sp == 0 ? 6 : 8, deg = sp == 0 ? 3 : 4, st = deg + 1;
 		if (c >= K * st) return;
@@ -67,13 +68,21 @@ namespace qb
 		const uint32_t n = uint32_t(gid % cx.n_max) + 1u;
 		if (job >= n_jobs) return;
 		const uint32_t sp = spin[job];
-		const int K = sp == 0 ? 6 : 8, deg = sp == 0 ? 3 : 4, st = deg + 1;
+		int K = sp == 0 ? 6 : 8, deg = sp == 0 ? 3 : 4;
+#ifdef __CUDA_ARCH__
+		// keep ONE copy of the loop body: without this the compiler clones and unrolls it per spin class and the kernel
+		// outgrows the instruction cache (measured: 75 % of its stall samples were instruction fetch)
+		asm volatile("" : "+r"(K), "+r"(deg));
+#endif
+		const int st = deg + 1;
 		const mpf<L>* c = coef + size_t(job) * QB_NCOEF;
 		mpf<L>* out = pv + size_t(gid) * 8;
+		QB_ROLL
 		for (int i = 0; i < K; ++i)
 		{
 			mpf<L> s;
 			copy(s, c[i * st + deg]);
+			QB_ROLL
 			for (int d = deg - 1; d >= 0; --d)
 			{
 				fast::mul_small(s, s, int64_t(n), cx.prec);

@@ -6,7 +6,7 @@
 //   kernels_g1.cuh  k_series      one thread per series job, n_max sequential steps                -> b[job][0..n_max]
 //   kernels_g2.cuh  k_scale       one thread per (table, n): the lambda+1 scaled coefficient arrays -> a[table][k][n]
 //                   k_horner      one thread per (table, k): Horner sum, times rho^q / k!           -> fr[table][k]
-//   kernels_g3.cuh  k_finish      one thread per table: rho->z matrix and the transverse recursion  -> g[table][dim_M]
+//   kernels_g3.cuh  k_rho_to_z, k_offdiag_val, k_offdiag_close: rho->z matrix and the transverse recursion, level by level -> g[table][dim_M]
 //   kernels_g4.cuh  k_pow         4^Delta and rho^(Delta-k);  k_vtod, k_fblock: v^d tables and F/H blocks
 // Numbers are records of L + 2 words (mpf<L>), arrays of records in HBM.  Arithmetic: mpf.cuh / fastops.cuh / hor.cuh /
 // block.cuh, all force-inlined (see mpf.cuh for why).
@@ -42,6 +42,15 @@ namespace qb
 		for (uint32_t n = 1; n <= cx.n_max; ++n)
 		{
 			const mpf<L>* p = pj + size_t(n - 1) * 8;
+#ifdef __CUDA_ARCH__
+			// the next step's polynomial values (8 contiguous records per lane) are pulled into L1 while this step computes
+			if (n < cx.n_max)
+			{
+				const char* q = reinterpret_cast<const char*>(p + 8);
+#pragma unroll
+				for (int o = 0; o < int(8 * sizeof(mpf<L>)); o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + o));
+			}
+#endif
 			mpf<L> sum, bn;
 			fast::mul(sum, p[1], bj[n - 1], prec);  // fma(0, p_1 b[n-1]) rounds like the product
 			for (int i = 2; i < K; ++i)

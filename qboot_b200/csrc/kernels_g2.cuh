@@ -6,7 +6,7 @@
 //   kernels_g1.cuh  k_series      one thread per series job, n_max sequential steps                -> b[job][0..n_max]
 //   kernels_g2.cuh  k_scale       one thread per (table, n): the lambda+1 scaled coefficient arrays -> a[table][k][n]
 //                   k_horner      one thread per (table, k): Horner sum, times rho^q / k!           -> fr[table][k]
-//   kernels_g3.cuh  k_finish      one thread per table: rho->z matrix and the transverse recursion  -> g[table][dim_M]
+//   kernels_g3.cuh  k_rho_to_z, k_offdiag_val, k_offdiag_close: rho->z matrix and the transverse recursion, level by level -> g[table][dim_M]
 //   kernels_g4.cuh  k_pow         4^Delta and rho^(Delta-k);  k_vtod, k_fblock: v^d tables and F/H blocks
 // Numbers are records of L + 2 words (mpf<L>), arrays of records in HBM.  Arithmetic: mpf.cuh / fastops.cuh / hor.cuh /
 // block.cuh, all force-inlined (see mpf.cuh for why).

@@ -6,7 +6,7 @@
 //   kernels_g1.cuh  k_series      one thread per series job, n_max sequential steps                -> b[job][0..n_max]
 //   kernels_g2.cuh  k_scale       one thread per (table, n): the lambda+1 scaled coefficient arrays -> a[table][k][n]
 //                   k_horner      one thread per (table, k): Horner sum, times rho^q / k!           -> fr[table][k]
-//   kernels_g3.cuh  k_finish      one thread per table: rho->z matrix and the transverse recursion  -> g[table][dim_M]
+//   kernels_g3.cuh  k_rho_to_z, k_offdiag_val, k_offdiag_close: rho->z matrix and the transverse recursion, level by level -> g[table][dim_M]
 //   kernels_g4.cuh  k_pow         4^Delta and rho^(Delta-k);  k_vtod, k_fblock: v^d tables and F/H blocks
 // Numbers are records of L + 2 words (mpf<L>), arrays of records in HBM.  Arithmetic: mpf.cuh / fastops.cuh / hor.cuh /
 // block.cuh, all force-inlined (see mpf.cuh for why).
@@ -20,23 +20,73 @@
 
 namespace qb
 {
+	// Stage a5 + a6 as a short sequence of WIDE kernels (every lane does the same amount of work):
+	//   k_rho_to_z        thread per (table, i): entry i of the rho -> z matrix-vector product (a dot product of lambda + 1
+	//                     terms, matrix.hpp:444-456); the i == 0 thread also leaves 4 C_2 of the table in qc[table]
+	//   k_offdiag_val     per dy-level n, thread per (table, dx = m): the part of the Casimir recursion that only reads
+	//                     levels n - 1 and n - 2 (context.cpp:72-121) -> written into the table slot (m, n)
+	//   k_offdiag_close   per dy-level n, thread per table: the same-level correction, sequential in m (context.cpp:122-131)
+	// lambda / 2 levels => 1 + 2 * (lambda / 2) launches per chunk; the kernel boundary is the level barrier.
 	template <int L>
-	__global__ void k_finish(DevCtx cx, int n_tables, const mpf<L>* __restrict__ delta, const uint32_t* __restrict__ spin,
-	                         const mpf<L>* __restrict__ S, const mpf<L>* __restrict__ P, const mpf<L>* __restrict__ fr,
-	                         mpf<L>* __restrict__ g)
+	__global__ void __launch_bounds__(128) k_rho_to_z(DevCtx cx, int n_tables, const mpf<L>* __restrict__ delta,
+	                                                  const uint32_t* __restrict__ spin, const mpf<L>* __restrict__ fr,
+	                                                  mpf<L>* __restrict__ g, mpf<L>* __restrict__ qc)
 	{
-		int t = blockIdx.x * blockDim.x + threadIdx.x;
+		const int lambda = int(cx.lambda), nk = lambda + 1, dimM = cf_dim(lambda), prec = cx.prec;
+		const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+		const int t = gid / nk, i = gid - t * nk;
 		if (t >= n_tables) return;
-		const int lambda = int(cx.lambda), nk = lambda + 1, dimM = cf_dim(lambda);
-		mpf<L>* f = g + size_t(t) * dimM;
 		const mpf<L>* M = reinterpret_cast<const mpf<L>*>(cx.mat);
 		mpf<L> z;
-		for (int i = 0; i <= lambda; ++i)
+		rho_to_z_entry(z, fr + size_t(t) * nk, 1, M, lambda, i, prec);
+		copy(g[size_t(t) * dimM + i], z);
+		if (i == 0)
 		{
-			rho_to_z_entry(z, fr + size_t(t) * nk, 1, M, lambda, i, cx.prec);
-			copy(f[i], z);
+			mpf<L> lD, q4;
+			copy(lD, delta[t]);
+			quad_casimir4(q4, lD, spin[t], cx.eps, prec);
+			copy(qc[t], q4);
 		}
-		expand_off_diag(f, 1, lambda, delta[t], spin[t], S[t], P[t], cx.eps, cx.prec);
+	}
+
+	template <int L>
+	__global__ void __launch_bounds__(128) k_offdiag_val(DevCtx cx, int n_tables, int n, const mpf<L>* __restrict__ S,
+	                                                     const mpf<L>* __restrict__ P, const mpf<L>* __restrict__ qc, mpf<L>* g)
+	{
+		const int lambda = int(cx.lambda), dimM = cf_dim(lambda), cnt = lambda - 2 * n + 1;
+		const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+		const int t = gid / cnt, m = gid - t * cnt;
+		if (t >= n_tables) return;
+		mpf<L>* f = g + size_t(t) * dimM;
+		mpf<L> lS, lP, q4, val;
+		copy(lS, S[t]);
+		copy(lP, P[t]);
+		copy(q4, qc[t]);
+		offdiag_val(val, f, 1, lambda, m, n, lS, lP, q4, cx.eps, cx.prec);
+		copy(f[cf_index(lambda, m, n)], val);
+	}
+
+	template <int L>
+	__global__ void __launch_bounds__(128) k_offdiag_close(DevCtx cx, int n_tables, int n, mpf<L>* g)
+	{
+		const int lambda = int(cx.lambda), dimM = cf_dim(lambda), cnt = lambda - 2 * n + 1;
+		const int t = blockIdx.x * blockDim.x + threadIdx.x;
+		if (t >= n_tables) return;
+		mpf<L>* f = g + size_t(t) * dimM + cf_index(lambda, 0, n);
+		mpf<L> p1, p2, p3, cur, val;
+		set_zero(p1);
+		set_zero(p2);
+		set_zero(p3);
+		QB_ROLL
+		for (int m = 0; m < cnt; ++m)
+		{
+			copy(val, f[m]);
+			offdiag_close(cur, m, val, p1, p2, p3, cx.prec);
+			copy(f[m], cur);
+			copy(p3, p2);
+			copy(p2, p1);
+			copy(p1, cur);
+		}
 	}
 
 }  // namespace qb

@@ -53,8 +53,8 @@ namespace qb
 	template <int L>
 	void launch_pow(const DevCtx& cx, int n_tables, const mpf<L>* delta, mpf<L>* pw, cudaStream_t st);
 	template <int L>
-	void launch_finish(const DevCtx& cx, int n_tables, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* S,
-	                   const mpf<L>* P, const mpf<L>* fr, mpf<L>* g, cudaStream_t st);
+	int launch_finish(const DevCtx& cx, int n_tables, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* S,
+	                  const mpf<L>* P, const mpf<L>* fr, mpf<L>* g, mpf<L>* qc, cudaStream_t st);  // returns #launches
 	template <int L>
 	void launch_vtod(const DevCtx& cx, int n_d, const mpf<L>* d, mpf<L>* v, cudaStream_t st);
 	template <int L>
