@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tables-per-gpu", type=int, default=int(os.environ.get("QB_BENCH_TABLES", "24548")))
+    ap.add_argument("--tables-per-gpu", type=int, default=int(os.environ.get("QB_BENCH_TABLES", "49096")))
     ap.add_argument("--ref-tables", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
