@@ -180,12 +180,15 @@ extern "C"
 	                    const uint32_t* P, uint32_t* out)
 	{
 		if (!h) return QB_ERR_BAD_ARG;
+		if (n > 0 && !out) return QB_ERR_BAD_ARG;
 		int rc = h->e->gblock_plan(n, spin, delta, S, P);
 		if (rc) return rc;
+		// every chunk is copied out as soon as it is finished, underneath the later chunks
+		h->e->fetch_dst = out;
 		rc = h->e->gblock_run();
+		h->e->fetch_dst = nullptr;
 		if (rc) return rc;
-		if (n > 0 && !out) return QB_ERR_BAD_ARG;
-		return h->e->gblock_fetch(out);
+		return qb_sync(h);
 	}
 	int qb_op_batch(qb_handle* h, int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c,
 	                const int64_t* ia, const int64_t* ib, uint32_t* out)

@@ -37,6 +37,9 @@ namespace qb
 		// per-kernel device times (ms) of the last gblock_run when timing is enabled: rec_coeffs, series, deriv, finish
 		bool timing = false;
 		float kernel_ms[4] = {0, 0, 0, 0};
+		// when set, gblock_run copies every chunk's tables to this host buffer as soon as the chunk is finished (on a copy
+		// stream, overlapping the later chunks); the handle's stream then also waits for the copies
+		uint32_t* fetch_dst = nullptr;
 		virtual int op_batch(int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c, const int64_t* ia,
 		                     const int64_t* ib, uint32_t* out) = 0;
 	};
@@ -45,6 +48,7 @@ namespace qb
 
 #ifdef QB_L
 // ------------------------------------------------------------------------------------------------------------------
+#include <thread>
 #include "hostmath.hpp"
 #include "block.cuh"
 #include "launch.cuh"
@@ -106,7 +110,8 @@ namespace qb
 		cudaStream_t lo_stream = nullptr;        // wide kernels of all chunks
 		std::vector<cudaStream_t> hi_streams;    // latency-bound kernels, one stream per chunk
 		std::vector<cudaEvent_t> dep_ev;         // 4 per chunk
-		cudaEvent_t fork_ev = nullptr;
+		cudaEvent_t fork_ev = nullptr, copy_done_ev = nullptr;
+		cudaStream_t copy_stream = nullptr;      // device -> host copies of finished chunks (fetch_dst)
 		int hi_priority = 0;
 		std::vector<int> job_of_table;  // first job of every table (+ sentinel)
 		std::vector<int> chunk_t;       // table boundaries of the chunks
@@ -278,6 +283,18 @@ namespace qb
 			add_si(onep, small, 1, prec);
 			neg(small);
 			add_si(onem, small, 1, prec);
+			// the divergence test is the only per-table arithmetic of the planner: fan it out over host threads
+			std::vector<uint8_t> diverges(static_cast<size_t>(n), 0);
+			{
+				const int nth = n >= 4096 ? int(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
+				auto work = [&](int lo, int hi) {
+					for (int t = lo; t < hi; ++t) diverges[size_t(t)] = (!is_zero(hd[t]) && is_divergent(hd[t], spin[t])) ? 1 : 0;
+				};
+				std::vector<std::thread> pool;
+				for (int k = 1; k < nth; ++k) pool.emplace_back(work, int(int64_t(n) * k / nth), int(int64_t(n) * (k + 1) / nth));
+				work(0, int(int64_t(n) / nth));
+				for (auto& th : pool) th.join();
+			}
 			for (int t = 0; t < n; ++t)
 			{
 				if ((hd[t].sk & 2u) || (hS[t].sk & 2u) || (hP[t].sk & 2u)) return -4;
@@ -292,7 +309,7 @@ namespace qb
 					jsp.push_back(spin[t]);
 					return int32_t(jd.size() - 1);
 				};
-				if (!is_zero(hd[t]) && is_divergent(hd[t], spin[t]))
+				if (diverges[size_t(t)])
 				{
 					// two evaluations at Delta (1 +- s), averaged                         (primary_op.hpp:53-56)
 					T dp, dm;
@@ -400,6 +417,14 @@ namespace qb
 			launches += launch_finish<L>(cx, r.t1 - r.t0, t_delta + r.t0, t_spin + r.t0, t_S + r.t0, t_P + r.t0,
 			                             d_fr.as<T>() + size_t(r.t0) * nk, d_g.as<T>() + size_t(r.t0) * dimM, d_qc.as<T>() + r.t0, st);
 		}
+		// device -> host copy of one finished chunk into fetch_dst
+		int copy_chunk_out(const Range& r, cudaStream_t st)
+		{
+			const size_t rec = sizeof(T) * size_t(cf_dim(int(lambda)));
+			QB_CU(cudaMemcpyAsync(reinterpret_cast<char*>(fetch_dst) + rec * size_t(r.t0), d_g.as<char>() + rec * size_t(r.t0),
+			                      rec * size_t(r.t1 - r.t0), cudaMemcpyDeviceToHost, st));
+			return 0;
+		}
 		// one chunk, all stages back to back on one stream, optionally with an event around every stage
 		int run_serial(int c, cudaStream_t st, cudaEvent_t* ev)
 		{
@@ -420,6 +445,8 @@ namespace qb
 			stage_finish(r, st);
 			if (int rc_ = debug_sync("k_finish")) return rc_;
 			if (timed) QB_CU(cudaEventRecord(ev[4], st));
+			if (fetch_dst)
+				if (int rc_ = copy_chunk_out(r, st)) return rc_;
 			return 0;
 		}
 		// The batch is cut into chunks.  The wide, throughput-bound kernels (coefficients, polynomial values, scale, Horner)
@@ -454,6 +481,8 @@ namespace qb
 				QB_CU(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
 				QB_CU(cudaStreamCreateWithPriority(&lo_stream, cudaStreamNonBlocking, pr_lo));
 				QB_CU(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+				QB_CU(cudaEventCreateWithFlags(&copy_done_ev, cudaEventDisableTiming));
+				QB_CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
 				hi_priority = pr_hi;
 			}
 			while (int(hi_streams.size()) < n_chunks)
@@ -490,9 +519,20 @@ namespace qb
 				QB_CU(cudaStreamWaitEvent(lo_stream, EV(c, 1), 0));
 				stage_deriv(r, lo_stream);
 				stage_finish(r, lo_stream);  // wide per-level kernels: same stream as the other wide stages
+				if (fetch_dst)
+				{
+					QB_CU(cudaEventRecord(EV(c, 3), lo_stream));
+					QB_CU(cudaStreamWaitEvent(copy_stream, EV(c, 3), 0));
+					if (int rc_ = copy_chunk_out(r, copy_stream)) return rc_;
+				}
 			}
-			QB_CU(cudaEventRecord(EV(0, 3), lo_stream));
-			QB_CU(cudaStreamWaitEvent(stream, EV(0, 3), 0));
+			QB_CU(cudaEventRecord(EV(0, 2), lo_stream));
+			QB_CU(cudaStreamWaitEvent(stream, EV(0, 2), 0));
+			if (fetch_dst)
+			{
+				QB_CU(cudaEventRecord(copy_done_ev, copy_stream));
+				QB_CU(cudaStreamWaitEvent(stream, copy_done_ev, 0));
+			}
 			QB_CU(cudaGetLastError());
 			return 0;
 		}

@@ -188,3 +188,37 @@ def test_device_fast_paths_vs_mpfr(ref, prec):
         bad = [i for i in range(len(want)) if not np.array_equal(want[i], got[i])]
         assert not bad, (name, bad[:5])
     eng.close()
+
+
+def test_chunked_streams_match_single_chunk(tmp_path):
+    """Batches larger than one chunk run their chunks over several streams (wide kernels on one stream, the series
+    recurrences on per-chunk priority streams, finished chunks copied out on a copy stream).  Scheduling must be
+    invisible in the output: a child process with a tiny chunk size (QB_CHUNK is read once per process) must produce
+    the tables of the single-chunk run bit for bit, through both the one-shot call and plan/run/fetch."""
+    import os
+    import subprocess
+    import sys
+
+    prec, n_max, lam, n = 600, 100, 11, 1500
+    rng = random.Random(11)
+    spin, delta, S, P = _random_inputs(rng, prec, n)
+    delta[5] = qb.from_fraction(Fraction(1, 2), prec)  # divergent for spin 0 in d = 3: the table owns two series jobs
+    spin[5] = 0
+    np.savez(tmp_path / "in.npz", spin=spin, delta=delta, S=S, P=P)
+    code = (
+        "import numpy as np, qboot_b200 as qb\n"
+        f"z = np.load(r'{tmp_path / 'in.npz'}')\n"
+        f"eng = qb.Engine({prec}).context({n_max}, {lam}, '3')\n"
+        "g = eng.gblock(z['spin'], z['delta'], z['S'], z['P'])\n"
+        "eng.plan(z['spin'], z['delta'], z['S'], z['P']); eng.run(); eng.sync(); g2 = eng.fetch()\n"
+        f"np.savez(r'{tmp_path / 'out.npz'}', g=g, g2=g2, launches=eng.launches)\n"
+    )
+    env = dict(os.environ, QB_CHUNK="256", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+    out = np.load(tmp_path / "out.npz")
+    eng = _engine(prec, n_max, lam)
+    want = eng.gblock(spin, delta, S, P)
+    eng.close()
+    assert int(out["launches"]) > 2 * 6 * 5  # several chunks really ran
+    assert np.array_equal(out["g"], want)
+    assert np.array_equal(out["g2"], want)
