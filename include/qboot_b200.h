@@ -69,13 +69,17 @@ int qb_block_dim(const qb_handle* h, int sym);
  *   spin[n]; delta, S, P: n records each (HOST memory); out: n * dim_M records (HOST memory) in the reference's
  *   flatten() order (dy-major, dx-minor, complex_function.hpp:72-81).
  * Unit operators (Delta = 0) and divergent operators (primary_op.hpp:68-77, averaged as in hor_recursion.cpp:21-28)
- * are handled as the reference handles them. */
+ * are handled as the reference handles them.
+ * Large batches are cut into chunks of 6144 tables; each finished chunk is copied to `out` while the later chunks still
+ * compute (pinned `out` makes that copy truly asynchronous; pageable memory works, more slowly).  Returns after the last
+ * copy has landed. */
 int qb_gblock_batch(qb_handle* h, int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S,
                     const uint32_t* P, uint32_t* out);
 
 /* The same in three steps, so that a caller (or a benchmark) can keep inputs and tables resident in HBM:
  *   plan  : host-side planning (b[0], divergence test, job list) + upload of the inputs
- *   run   : all kernels, asynchronous on the handle's stream
+ *   run   : all kernels, asynchronous; chunks of the batch are spread over internal streams that fork from and join
+ *           the handle's stream, so work queued on that stream before / after is ordered before / after
  *   fetch : device -> host copy of the n * dim_M records                                                  */
 int qb_gblock_plan(qb_handle* h, int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S,
                    const uint32_t* P);
@@ -97,10 +101,11 @@ int qb_fblock_batch(qb_handle* h, int m, const int32_t* table_idx, int n_d, cons
                     const int32_t* sym, uint32_t* out);
 
 /* Measurement support.  qb_set_timing(h, 1) brackets each kernel of qb_gblock_run with CUDA events on the handle's
- * stream; qb_kernel_times synchronises and returns the device times in ms of the last run:
- * [0] recurrence coefficients, [1] series recurrence, [2] rho-derivative chains, [3] rho->z + transverse recursion.
- * qb_imad_peak measures the integer multiply-add issue rate of this GPU (dependency-free mad.wide.u32 chains at full
- * occupancy) in limb-MACs per second -- the denominator of the roofline for this path. */
+ * stream (chunks then run back to back on that one stream); qb_kernel_times synchronises and returns the device times
+ * in ms of the last run: [0] recurrence coefficients, [1] polynomial values + series recurrence, [2] powers +
+ * rho-derivative chains (scale, Horner), [3] rho->z + transverse recursion.
+ * qb_imad_peak measures the limb-product issue rate of this GPU (dependency-free IMAD.WIDE.U32 chains, 32 x 32 + 64 ->
+ * 64, at full occupancy) in limb-MACs per second -- the denominator of the roofline for this path. */
 int qb_set_timing(qb_handle* h, int on);
 int qb_kernel_times(qb_handle* h, float* ms4);
 int qb_imad_peak(qb_handle* h, int iters, double* macs_per_s);

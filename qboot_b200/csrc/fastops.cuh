@@ -209,6 +209,176 @@ namespace qb
 			st = low;
 		}
 
+		// Short product: the same frame as mul_top from fewer limb products.  Products a_i b_k whose position i + k lies
+		// below T = L - 5 cannot reach the frame except through carries, so most of them are skipped: the rows are cut into
+		// segments of R = 8, and the rows of a segment only visit the columns k >= kmin(segment) (a static staircase that
+		// covers every product at position >= T).  With S the exact sum of the visited products, the frame and the two
+		// limbs f4, f5 below it (positions L-4, L-5) are read off S, and
+		//     a b  =  [frame | f4 | f5]  +  r,     0 <= r < L units of f4
+		// (skipped products < (L-5)(1+2^-31) units of f4, limbs of S dropped below f5 < one unit of f5).  Hence the frame
+		// is exact unless f4 >= 2^32 - L, and the remainder below the frame is known to be nonzero when f4 | f5 != 0.  In
+		// the two undecidable cases (probability ~L 2^-32 for full-width operands) the function returns false and the caller
+		// takes the full product.  A short multiplicand b (all limbs below position L - 5 zero) is recognised: then nothing
+		// nonzero was skipped and f4 = f5 = 0 means an exact frame.  st: as mul_top.
+		template <int L>
+		struct ShortPlan
+		{
+			static constexpr int LP = (L + 1) & ~1, T = L - 5, R = 8, NSEG = (LP + R - 1) / R;
+			static constexpr int i0(int s) { return s * R; }
+			static constexpr int i1(int s) { return (s * R + R < LP) ? s * R + R : LP; }
+			static constexpr int kmin(int s) { return T - (i1(s) - 1) <= 0 ? 0 : ((T - (i1(s) - 1)) & ~1); }
+			// lowest product position visited by segments 0 .. s
+			static constexpr int abs_low(int s) { return s == 0 ? i0(0) + kmin(0) : (i0(s) + kmin(s) < abs_low(s - 1) ? i0(s) + kmin(s) : abs_low(s - 1)); }
+			static constexpr bool retire(int s) { return (i1(s) - 1) >= (T - 1); }
+			// window entries below jlo are zero throughout segment s
+			static constexpr int jlo(int s) { return (retire(s) || abs_low(s) - (i1(s) - 2) <= 0) ? 0 : ((abs_low(s) - (i1(s) - 2)) & ~1); }
+		};
+
+		// rows [i0, i1) of segment S, then the following segments
+		template <int L, int S>
+		QB_HD QB_INLINE void mul_short_seg(uint32_t (&EV)[((L + 1) & ~1) + 4], uint32_t (&OD)[((L + 1) & ~1) + 2], const uint32_t (&b)[(L + 1) & ~1],
+		                                   const uint32_t* a, uint32_t& n0, uint32_t& n1, uint32_t (&g)[6])
+		{
+			using PL = ShortPlan<L>;
+			constexpr int LP = PL::LP, i0 = PL::i0(S), i1 = PL::i1(S), kmin = PL::kmin(S), jlo = PL::jlo(S);
+			constexpr bool retire = PL::retire(S);
+			constexpr int ms = jlo >= 2 ? jlo - 2 : 0;  // first window entry the fold has to produce
+			static_assert(kmin % 2 == 0 && jlo % 2 == 0 && (!retire || kmin == 0) && jlo <= kmin, "short-product staircase");
+#pragma unroll 1
+			for (int i = i0; i < i1; i += 2)
+			{
+				const uint32_t a0 = n0, a1 = n1;
+				if (i + 2 < LP)
+				{
+					n0 = a[i + 2];
+					n1 = (i + 3 < L) ? a[i + 3] : 0u;
+				}
+				QB_CY_DECL
+				// row i, even columns -> EV
+				QB_MAD_FIRST(EV[kmin], EV[kmin + 1], a0, b[kmin]);
+#pragma unroll
+				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(EV[k], EV[k + 1], a0, b[k]);
+				QB_ADDC_CC(EV[LP]);
+				QB_ADDC_END(EV[LP + 1]);
+				// row i, odd columns -> OD (fresh)
+#pragma unroll
+				for (int k = kmin; k < LP; k += 2)
+				{
+					uint64_t t = uint64_t(a0) * uint64_t(b[k + 1]);
+					OD[k] = uint32_t(t);
+					OD[k + 1] = uint32_t(t >> 32);
+				}
+				OD[LP] = 0u;
+				OD[LP + 1] = 0u;
+				// row i+1, even columns -> OD
+				QB_MAD_FIRST(OD[kmin], OD[kmin + 1], a1, b[kmin]);
+#pragma unroll
+				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(OD[k], OD[k + 1], a1, b[k]);
+				QB_ADDC_END(OD[LP]);
+				// row i+1, odd columns -> EV shifted by two
+				QB_MAD_FIRST(EV[kmin + 2], EV[kmin + 3], a1, b[kmin + 1]);
+#pragma unroll
+				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(EV[k + 2], EV[k + 3], a1, b[k + 1]);
+				QB_ADDC_CC(EV[LP + 2]);
+				QB_ADDC_END(EV[LP + 3]);
+				// fold OD into EV and slide the window by two limbs; positions i and i+1 leave the window
+				if (retire)
+				{
+					g[4] = g[0];
+					g[5] = g[1];
+					g[0] = g[2];
+					g[1] = g[3];
+					g[2] = EV[0];
+					QB_ADD_FIRST(g[3], EV[1], OD[0]);
+#pragma unroll
+					for (int m = 0; m < LP + 2; ++m)
+					{
+						const uint32_t o = (m + 1 < LP + 2) ? OD[m + 1] : 0u;
+						QB_ADD_NEXT(EV[m], EV[m + 2], o);
+					}
+				}
+				else if (ms == 0)
+				{
+					// positions i, i+1 are below everything that is read later, but their carry is kept
+					uint32_t dump;
+					QB_ADD_FIRST(dump, EV[1], (0 >= kmin ? OD[0] : 0u));
+					(void)dump;
+#pragma unroll
+					for (int m = 0; m < LP + 2; ++m)
+					{
+						const uint32_t o = (m + 1 >= kmin && m + 1 < LP + 2) ? OD[m + 1] : 0u;
+						QB_ADD_NEXT(EV[m], EV[m + 2], o);
+					}
+				}
+				else
+				{
+					// entries below jlo are zero (and OD below kmin >= jlo is not written in this segment)
+					QB_ADD_FIRST(EV[ms], EV[ms + 2], (ms + 1 >= kmin ? OD[ms + 1] : 0u));
+#pragma unroll
+					for (int m = ms + 1; m < LP + 2; ++m)
+					{
+						const uint32_t o = (m + 1 >= kmin && m + 1 < LP + 2) ? OD[m + 1] : 0u;
+						QB_ADD_NEXT(EV[m], EV[m + 2], o);
+					}
+				}
+				EV[LP + 2] = 0u;
+				EV[LP + 3] = 0u;
+			}
+			if constexpr (S + 1 < PL::NSEG) mul_short_seg<L, S + 1>(EV, OD, b, a, n0, n1, g);
+		}
+
+		template <int L>
+		QB_HD QB_INLINE bool mul_top_short(uint32_t* X, uint32_t& st, const uint32_t* a, const uint32_t* rb)
+		{
+			constexpr int LP = (L + 1) & ~1;  // even
+			uint32_t b[LP], EV[LP + 4], OD[LP + 2];
+#pragma unroll
+			for (int j = 0; j < LP; ++j) b[j] = j < L ? rb[j] : 0u;
+#pragma unroll
+			for (int j = 0; j < LP + 4; ++j) EV[j] = 0u;
+#pragma unroll
+			for (int j = 0; j < LP + 2; ++j) OD[j] = 0u;
+			uint32_t g[6] = {0u, 0u, 0u, 0u, 0u, 0u};  // g[0..3]: the four positions below the window; g[4], g[5]: the two below those
+			uint32_t n0 = a[0], n1 = (1 < L) ? a[1] : 0u;
+			mul_short_seg<L, 0>(EV, OD, b, a, n0, n1, g);
+			uint32_t f4, f5;
+			if (L % 2 == 0)
+			{
+				// positions L-4 .. L-1 are g[0..3], L-6 and L-5 are g[4], g[5]; EV[j] <-> position L + j
+				f4 = g[0];
+				f5 = g[5];
+				X[0] = g[1];
+				X[1] = g[2];
+				X[2] = g[3];
+#pragma unroll
+				for (int j = 0; j < L; ++j) X[3 + j] = EV[j];
+			}
+			else
+			{
+				// LP = L + 1: positions L-3 .. L are g[0..3], L-5 and L-4 are g[4], g[5]; EV[j] <-> position L + 1 + j
+				f4 = g[5];
+				f5 = g[4];
+				X[0] = g[0];
+				X[1] = g[1];
+				X[2] = g[2];
+				X[3] = g[3];
+#pragma unroll
+				for (int j = 0; j + 4 < L + 3; ++j) X[4 + j] = EV[j];
+			}
+			st = f4 | f5;
+			if (st == 0u)
+			{
+				// Nothing is known about the remainder -- unless b is short (a machine number, a decimal with few digits, ...):
+				// when its limbs below position L - 5 are all zero every skipped product vanishes and the product is exact
+				// from position L - 5 up, so the remainder below the frame really is zero.
+				uint32_t lowb = 0u;
+#pragma unroll
+				for (int j = 0; j + 5 < L; ++j) lowb |= b[j];
+				return lowb == 0u;
+			}
+			return f4 < 0xFFFFFFFFu - uint32_t(L);
+		}
+
 		// Round the frame X[0 .. L+2) (value 0.X * 2^e, plus a positive remainder below the last bit when st != 0) into r.
 		// Requires fewer than 64 leading zero bits with X[L+1] | X[L] != 0; returns false otherwise (nothing written).
 		template <int L>
@@ -477,7 +647,7 @@ namespace qb
 			for (int j = 0; j < L; ++j) rb[j] = b.m[j];
 			const uint32_t sgn = (a.sk ^ b.sk) & SIGN_BIT;
 			int32_t e = a.exp + b.exp;
-			mul_top<L>(X, st, a.m, rb);
+			if (!mul_top_short<L>(X, st, a.m, rb)) mul_top<L>(X, st, a.m, rb);
 			if ((X[L + 2] & 0x80000000u) == 0u)
 			{
 #pragma unroll
@@ -503,7 +673,7 @@ namespace qb
 			for (int j = 0; j < L; ++j) rb[j] = b.m[j];
 			const uint32_t sgn = (a.sk ^ b.sk) & SIGN_BIT;
 			int32_t e = a.exp + b.exp;
-			mul_top<L>(X, st, a.m, rb);
+			if (!mul_top_short<L>(X, st, a.m, rb)) mul_top<L>(X, st, a.m, rb);
 			if ((X[L + 2] & 0x80000000u) == 0u)
 			{
 #pragma unroll

@@ -10,6 +10,7 @@ tests feed identical records to both sides.
 """
 from __future__ import annotations
 
+import functools
 import math
 from fractions import Fraction
 
@@ -24,10 +25,25 @@ def num_poles(numax: int, spin: int) -> int:
     return numax + min(numax, spin) // 2
 
 
+@functools.lru_cache(maxsize=None)
+def _sample_points(D: int):
+    """x_k = pi^2 (4k-1)^2 / (-64 (D+1) ln(3 - 2 sqrt 2)), k = 0..D (conformal_scale.hpp:105-116) to 1600 bits, as exact
+    rationals: like the reference's, the sample points carry full-width mantissas at every supported precision"""
+    import mpmath
+
+    with mpmath.workprec(1600):
+        c = mpmath.pi ** 2 / (-64 * (D + 1) * mpmath.log(3 - 2 * mpmath.sqrt(2)))
+        out = []
+        for k in range(D + 1):
+            v = c * (4 * k - 1) ** 2
+            man, exp = int(v.man), int(v.exp)
+            out.append((-1 if v < 0 else 1) * (Fraction(man) * Fraction(2) ** exp))
+    return tuple(out)
+
+
 def sample_deltas(spin: int, lam: int, numax: int, gap: Fraction):
     D = num_poles(numax, spin) + lam
-    xs = [math.pi ** 2 * (4 * k - 1) ** 2 / (-64.0 * (D + 1) * LN_RHO) for k in range(D + 1)]
-    return [Fraction(x) + gap for x in xs]
+    return [x + gap for x in _sample_points(D)]
 
 
 def mixed_ising_keys(prec: int, lam: int, numax: int, maxspin: int, ds="0.5181489", de="1.412625"):

@@ -202,3 +202,47 @@ def test_fast_paths_vs_mpfr(hostemu, ref, prec):
         got = _fast(hostemu, FAST[name], prec, **kw)
         bad = [i for i in range(len(want)) if not np.array_equal(want[i], got[i])]
         assert not bad, (name, bad[:5])
+
+
+@pytest.mark.parametrize("prec", [512, 608, 800, 1024, 1216, 1536])
+def test_short_product_boundaries(hostemu, ref, prec):
+    """The multiply fast path builds its L+3-limb frame from a SHORT product (fastops.cuh::mul_top_short) and must notice
+    when the skipped low limb products could matter.  Operands are constructed so that the low limbs of the exact product
+    are chosen at will (a = target * b^-1 modulo 2^(32 (L-3)), b odd): the two limbs just below the frame sit on and around
+    every decision boundary (0, L, 2^32 - L, 2^32 - 1) over all-zero, all-one and random tails."""
+    rng = random.Random(prec)
+    L = prec // 32
+    low_bits = 32 * (L - 3)
+    mod = 1 << low_bits
+    M32 = 0xFFFFFFFF
+    f4s = [0, 1, 2, L - 6, L - 5, L - 4, L - 3, L, L + 1, M32 - L - 2, M32 - L - 1, M32 - L, M32 - L + 1, M32 - 4, M32 - 1, M32]
+    A, B = [], []
+    for f4 in f4s:
+        for f5 in (0, 1, M32, rng.getrandbits(32)):
+            for tail in ("zeros", "ones", "random"):
+                nb = 32 * (L - 5)
+                t = {"zeros": 0, "ones": (1 << nb) - 1, "random": rng.getrandbits(nb)}[tail]
+                target = (f4 << (32 * (L - 4))) | (f5 << (32 * (L - 5))) | t
+                b = rng.getrandbits(prec) | (1 << (prec - 1)) | 1
+                a_low = (target * pow(b, -1, mod)) % mod
+                a = (rng.getrandbits(96) | (1 << 95)) << low_bits | a_low
+                assert (a * b) % mod == target
+                A.append(ref.from_int_exp(rng.getrandbits(1), a, rng.randint(-40, 40) - prec, prec))
+                B.append(ref.from_int_exp(rng.getrandbits(1), b, rng.randint(-40, 40) - prec, prec))
+    # short operands (machine numbers, few-digit decimals): the limbs just below the frame are exactly zero
+    for _ in range(60):
+        wide = rng.getrandbits(prec) | (1 << (prec - 1)) | 1
+        nbits = rng.choice([1, 2, 24, 53, 64, 96, 128, 160, 32 * 5, 32 * 5 + 1, 32 * 6])
+        short = (rng.getrandbits(nbits) | (1 << (nbits - 1)) | 1) << (prec - nbits)
+        x, y = (wide, short) if rng.random() < 0.7 else (short, wide)
+        A.append(ref.from_int_exp(rng.getrandbits(1), x, rng.randint(-40, 40) - prec, prec))
+        B.append(ref.from_int_exp(rng.getrandbits(1), y, rng.randint(-40, 40) - prec, prec))
+    A, B = np.stack(A), np.stack(B)
+    from tests.golden.make_golden import rnd_num
+
+    C = np.stack([rnd_num(rng, prec, -80, 80) for _ in range(len(A))])
+    for name, kw in (("mul", dict(a=A, b=B)), ("mul", dict(a=B, b=A)), ("fma", dict(a=A, b=B, c=C))):
+        want = ref.op(name, prec, **kw)
+        got = _fast(hostemu, FAST[name], prec, **kw)
+        bad = [i for i in range(len(want)) if not np.array_equal(want[i], got[i])]
+        assert not bad, (name, bad[:5])
