@@ -341,7 +341,7 @@ namespace qb
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
-			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (n1 + 1) * nt) || d_qc.ensure(sizeof(T) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * a_slot_records) ||
+			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (2 * n1 + 1) * nt) || d_qc.ensure(sizeof(T) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * a_slot_records) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;
 			t_delta = d_in.as<T>();
@@ -397,16 +397,16 @@ namespace qb
 		}
 		void stage_pow(const Range& r, cudaStream_t st)
 		{
-			launch_pow<L>(cx, r.t1 - r.t0, t_delta + r.t0, d_pw.as<T>() + size_t(r.t0) * (size_t(lambda) + 2), st);
+			launch_pow<L>(cx, r.t1 - r.t0, t_delta + r.t0, d_pw.as<T>() + size_t(r.t0) * (2 * size_t(lambda) + 3), st);
 			++launches;
 		}
 		void stage_deriv(const Range& r, cudaStream_t st)
 		{
 			const size_t nk = size_t(lambda) + 1;
-			T* pw = d_pw.as<T>() + size_t(r.t0) * (nk + 1);
+			T* pw = d_pw.as<T>() + size_t(r.t0) * (2 * nk + 1);
 			// TableRef holds absolute job indices: hand the whole series array.  One scratch slot: the (scale, horner)
 			// pairs of all chunks are serialised on one stream.
-			launch_scale<L>(cx, r.t1 - r.t0, d_tref.as<TableRef>() + r.t0, t_delta + r.t0, d_b.as<T>(), pw, d_a.as<T>(), st);
+			launch_scale<L>(cx, r.t1 - r.t0, d_tref.as<TableRef>() + r.t0, d_b.as<T>(), pw, d_a.as<T>(), st);
 			++launches;
 			launch_horner<L>(cx, r.t1 - r.t0, d_a.as<T>(), pw, d_fr.as<T>() + size_t(r.t0) * nk, st);
 			++launches;

@@ -121,7 +121,9 @@ namespace qb
 		//   EV[m] <-> position i + m,  OD[m] <-> position i + 1 + m
 		//   row i   : a_i b_k (k even) -> EV[k], EV[k+1];   a_i b_k (k odd) -> OD[k-1], OD[k]
 		//   row i+1 : a_{i+1} b_k (k even) -> OD[k], OD[k+1];   (k odd) -> EV[k+1], EV[k+2]
-		template <int L>
+		// AS: distance in words between consecutive limbs of a (1 for a record; the block size when the kernel stages a
+		// in shared memory, limb-major, so that the per-row fetch never touches thread-local memory).
+		template <int L, int AS = 1>
 		QB_HD QB_INLINE void mul_top(uint32_t* X, uint32_t& st, const uint32_t* a, const uint32_t* rb)
 		{
 			constexpr int LP = (L + 1) & ~1;  // even
@@ -133,15 +135,15 @@ namespace qb
 			uint32_t g0 = 0u, g1 = 0u, g2 = 0u, g3 = 0u, low = 0u;
 			// the two multiplier limbs of the NEXT row pair are fetched one iteration ahead: a may live in global or local
 			// memory and the rolled loop would otherwise expose that load's latency once per row pair
-			uint32_t n0 = a[0], n1 = (1 < L) ? a[1] : 0u;
+			uint32_t n0 = a[0], n1 = (1 < L) ? a[AS] : 0u;
 #pragma unroll 1
 			for (int i = 0; i < LP; i += 2)
 			{
 				const uint32_t a0 = n0, a1 = n1;
 				if (i + 2 < LP)
 				{
-					n0 = a[i + 2];
-					n1 = (i + 3 < L) ? a[i + 3] : 0u;
+					n0 = a[(i + 2) * AS];
+					n1 = (i + 3 < L) ? a[(i + 3) * AS] : 0u;
 				}
 				QB_CY_DECL
 				// row i, even columns -> EV
@@ -235,7 +237,7 @@ namespace qb
 		};
 
 		// rows [i0, i1) of segment S, then the following segments
-		template <int L, int S>
+		template <int L, int S, int AS>
 		QB_HD QB_INLINE void mul_short_seg(uint32_t (&EV)[((L + 1) & ~1) + 4], uint32_t (&OD)[((L + 1) & ~1) + 2], const uint32_t (&b)[(L + 1) & ~1],
 		                                   const uint32_t* a, uint32_t& n0, uint32_t& n1, uint32_t (&g)[6])
 		{
@@ -250,8 +252,8 @@ namespace qb
 				const uint32_t a0 = n0, a1 = n1;
 				if (i + 2 < LP)
 				{
-					n0 = a[i + 2];
-					n1 = (i + 3 < L) ? a[i + 3] : 0u;
+					n0 = a[(i + 2) * AS];
+					n1 = (i + 3 < L) ? a[(i + 3) * AS] : 0u;
 				}
 				QB_CY_DECL
 				// row i, even columns -> EV
@@ -324,10 +326,10 @@ namespace qb
 				EV[LP + 2] = 0u;
 				EV[LP + 3] = 0u;
 			}
-			if constexpr (S + 1 < PL::NSEG) mul_short_seg<L, S + 1>(EV, OD, b, a, n0, n1, g);
+			if constexpr (S + 1 < PL::NSEG) mul_short_seg<L, S + 1, AS>(EV, OD, b, a, n0, n1, g);
 		}
 
-		template <int L>
+		template <int L, int AS = 1>
 		QB_HD QB_INLINE bool mul_top_short(uint32_t* X, uint32_t& st, const uint32_t* a, const uint32_t* rb)
 		{
 			constexpr int LP = (L + 1) & ~1;  // even
@@ -339,8 +341,8 @@ namespace qb
 #pragma unroll
 			for (int j = 0; j < LP + 2; ++j) OD[j] = 0u;
 			uint32_t g[6] = {0u, 0u, 0u, 0u, 0u, 0u};  // g[0..3]: the four positions below the window; g[4], g[5]: the two below those
-			uint32_t n0 = a[0], n1 = (1 < L) ? a[1] : 0u;
-			mul_short_seg<L, 0>(EV, OD, b, a, n0, n1, g);
+			uint32_t n0 = a[0], n1 = (1 < L) ? a[AS] : 0u;
+			mul_short_seg<L, 0, AS>(EV, OD, b, a, n0, n1, g);
 			uint32_t f4, f5;
 			if (L % 2 == 0)
 			{
@@ -633,21 +635,18 @@ namespace qb
 			return round_frame<L>(r, sb, er, R, st, prec);
 		}
 
-		// r = RN(a * b); a's limbs are read row by row from wherever a lives, b's limbs are pulled into registers
-		template <int L>
-		QB_HD QB_INLINE void mul(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec)
+		// normalised product frame of two regular numbers: X[0 .. L+3) with the top bit of X[L+2] set, exponent e, st = OR of
+		// everything below X[1] (X[0] included); a's limbs are read row by row from a_limbs (stride AS), b's limbs are
+		// pulled into registers
+		template <int L, int AS>
+		QB_HD QB_INLINE void product_frame(uint32_t* X, uint32_t& st, int32_t& e, const uint32_t* a_limbs, int32_t a_exp,
+		                                   const mpf<L>& b)
 		{
-			if ((a.sk & 3u) != K_REG || (b.sk & 3u) != K_REG)
-			{
-				qb::mul(r, a, b, prec);
-				return;
-			}
-			uint32_t rb[L], X[L + 3], st;
+			uint32_t rb[L];
 #pragma unroll
 			for (int j = 0; j < L; ++j) rb[j] = b.m[j];
-			const uint32_t sgn = (a.sk ^ b.sk) & SIGN_BIT;
-			int32_t e = a.exp + b.exp;
-			if (!mul_top_short<L>(X, st, a.m, rb)) mul_top<L>(X, st, a.m, rb);
+			e = a_exp + b.exp;
+			if (!mul_top_short<L, AS>(X, st, a_limbs, rb)) mul_top<L, AS>(X, st, a_limbs, rb);
 			if ((X[L + 2] & 0x80000000u) == 0u)
 			{
 #pragma unroll
@@ -656,7 +655,40 @@ namespace qb
 				e -= 1;
 			}
 			st |= X[0];
-			round_frame<L>(r, sgn, e, X + 1, st, prec);  // top bit set: always succeeds
+		}
+
+		// r = RN(a * b) for REGULAR a given as (sign/kind word, exponent, limbs at stride AS) and regular b
+		template <int L, int AS>
+		QB_HD QB_INLINE void mul_strided(mpf<L>& r, uint32_t a_sk, int32_t a_exp, const uint32_t* a_limbs, const mpf<L>& b, int prec)
+		{
+			uint32_t X[L + 3], st;
+			int32_t e;
+			product_frame<L, AS>(X, st, e, a_limbs, a_exp, b);
+			round_frame<L>(r, (a_sk ^ b.sk) & SIGN_BIT, e, X + 1, st, prec);  // top bit set: always succeeds
+		}
+
+		// r = RN(a * b)
+		template <int L>
+		QB_HD QB_INLINE void mul(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec)
+		{
+			if ((a.sk & 3u) != K_REG || (b.sk & 3u) != K_REG)
+			{
+				qb::mul(r, a, b, prec);
+				return;
+			}
+			mul_strided<L, 1>(r, a.sk, a.exp, a.m, b, prec);
+		}
+
+		// r = RN(a * b + c) for REGULAR a (strided limbs, see mul_strided), regular b and c.  Returns false when the frame
+		// cannot decide the rounding (addround); the caller then owns the generic fall-back.
+		template <int L, int AS>
+		QB_HD QB_INLINE bool fma_strided(mpf<L>& r, uint32_t a_sk, int32_t a_exp, const uint32_t* a_limbs, const mpf<L>& b,
+		                                 const mpf<L>& c, int prec)
+		{
+			uint32_t X[L + 3], st;
+			int32_t e;
+			product_frame<L, AS>(X, st, e, a_limbs, a_exp, b);
+			return addround<L>(r, (a_sk ^ b.sk) & SIGN_BIT, e, X + 1, st, c, prec);
 		}
 
 		// r = RN(a * b + c)
@@ -668,21 +700,7 @@ namespace qb
 				qb::fma(r, a, b, c, prec);
 				return;
 			}
-			uint32_t rb[L], X[L + 3], st;
-#pragma unroll
-			for (int j = 0; j < L; ++j) rb[j] = b.m[j];
-			const uint32_t sgn = (a.sk ^ b.sk) & SIGN_BIT;
-			int32_t e = a.exp + b.exp;
-			if (!mul_top_short<L>(X, st, a.m, rb)) mul_top<L>(X, st, a.m, rb);
-			if ((X[L + 2] & 0x80000000u) == 0u)
-			{
-#pragma unroll
-				for (int k = L + 2; k >= 1; --k) X[k] = (X[k] << 1) | (X[k - 1] >> 31);
-				X[0] <<= 1;
-				e -= 1;
-			}
-			st |= X[0];
-			if (!addround<L>(r, sgn, e, X + 1, st, c, prec)) qb::fma(r, a, b, c, prec);
+			if (!fma_strided<L, 1>(r, a.sk, a.exp, a.m, b, c, prec)) qb::fma(r, a, b, c, prec);
 		}
 
 		// r = RN(a + b) (negate_b: a - b)

@@ -49,38 +49,21 @@ namespace qb
 		k_series<QB_L><<<(n_jobs + threads - 1) / threads, threads, 0, st>>>(cx, n_jobs, delta, spin, b0, pv, b);
 	}
 #elif QB_KGROUP == 2
-	template <class K>
-	static size_t co_residency_pad(K kernel)
-	{
-		if (!std::getenv("QB_PAD")) return 0;  // experiment knob; off by default (measured slower)
-		const size_t bytes = 72 * 1024;
-		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) != cudaSuccess)
-		{
-			cudaGetLastError();
-			return 0;
-		}
-		return bytes;
-	}
 	template <>
-	void launch_scale<QB_L>(const DevCtx& cx, int n_tables, const TableRef* tref, const mpf<QB_L>* delta, const mpf<QB_L>* b,
-	                        const mpf<QB_L>* pw, mpf<QB_L>* a, cudaStream_t st)
+	void launch_scale<QB_L>(const DevCtx& cx, int n_tables, const TableRef* tref, const mpf<QB_L>* b, const mpf<QB_L>* pw,
+	                        mpf<QB_L>* a, cudaStream_t st)
 	{
-		int threads = 128;
+		int threads = QB_DERIV_THREADS;
 		int64_t total = int64_t(n_tables) * (cx.n_max + 1);
-		// Unused dynamic shared memory caps the kernel at 3 CTAs per SM: the fourth would take the last registers, and the
-		// latency-bound one-thread-per-table kernels of the neighbouring streams (k_series, k_pow, k_finish) could not
-		// co-reside.  Costs nothing: the kernel is far from occupancy-bound.
-		static const size_t pad = co_residency_pad(k_scale<QB_L>);
-		k_scale<QB_L><<<unsigned((total + threads - 1) / threads), threads, pad, st>>>(cx, n_tables, tref, delta, b, pw, a);
+		k_scale<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, tref, b, pw, a);
 	}
 	template <>
 	void launch_horner<QB_L>(const DevCtx& cx, int n_tables, const mpf<QB_L>* a, const mpf<QB_L>* pw, mpf<QB_L>* fr,
 	                         cudaStream_t st)
 	{
-		int threads = 128;
+		int threads = QB_DERIV_THREADS;
 		int64_t total = int64_t(n_tables) * (int(cx.lambda) + 1);
-		static const size_t pad = co_residency_pad(k_horner<QB_L>);
-		k_horner<QB_L><<<unsigned((total + threads - 1) / threads), threads, pad, st>>>(cx, n_tables, a, pw, fr);
+		k_horner<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, a, pw, fr);
 	}
 #elif QB_KGROUP == 3
 	template <>

@@ -20,17 +20,42 @@
 
 namespace qb
 {
+	// Both kernels of this stage keep the running value of their chain -- the row operand of every product -- in SHARED
+	// memory, limb-major (limb j of thread x at sh[j * 128 + x], conflict-free), with its sign and exponent in registers:
+	// the rolled product loop fetches two limbs per iteration, and a thread-local record would live in local memory,
+	// whose footprint (resident threads x stack) overflows L1 and spills to DRAM (measured: 7 GB per launch).
+	constexpr int QB_DERIV_THREADS = 128;
+
+	template <int L>
+	__device__ __forceinline__ void chain_store(uint32_t* my, uint32_t& sk, int32_t& exp, const mpf<L>& v)
+	{
+		sk = v.sk;
+		exp = v.exp;
+#pragma unroll
+		for (int j = 0; j < L; ++j) my[j * QB_DERIV_THREADS] = v.m[j];
+	}
+	template <int L>
+	__device__ __forceinline__ void chain_load(mpf<L>& v, const uint32_t* my, uint32_t sk, int32_t exp)
+	{
+		v.sk = sk;
+		v.exp = exp;
+#pragma unroll
+		for (int j = 0; j < L; ++j) v.m[j] = my[j * QB_DERIV_THREADS];
+	}
+
 	// rho-derivative stage, part 1: every scaled coefficient array a_k[n], k = 0..lambda (reference: h *= 4^Delta,
 	// src/hor_recursion.cpp:43, then lambda times RealFunctionWithPower::derivate, real_function.hpp:236-240):
-	//   a_0[n] = b[n] * 4^Delta,   a_k[n] = a_{k-1}[n] * (q_{k-1} + n),   q_k = q_{k-1} - 1,  q_0 = Delta
+	//   a_0[n] = b[n] * 4^Delta,   a_k[n] = a_{k-1}[n] * (q_{k-1} + n),   q_k = q_{k-1} - 1,  q_0 = Delta  (q_k from k_pow)
 	// One thread per (table, n) walks k: no dependency between threads, no barrier.  Layout a[table][k][n] (n fastest) so
 	// that part 2 streams each chain contiguously.  The arrays (lambda+1 times the series, ~1.1 MB per table at the
 	// north-star size) live in HBM: written once here, read once by k_horner.
 	template <int L>
-	__global__ void __launch_bounds__(128, 4)
-	    k_scale(DevCtx cx, int n_tables, const TableRef* __restrict__ tref, const mpf<L>* __restrict__ delta,
-	            const mpf<L>* __restrict__ b, const mpf<L>* __restrict__ pw, mpf<L>* __restrict__ a)
+	__global__ void __launch_bounds__(QB_DERIV_THREADS, 4)
+	    k_scale(DevCtx cx, int n_tables, const TableRef* __restrict__ tref, const mpf<L>* __restrict__ b,
+	            const mpf<L>* __restrict__ pw, mpf<L>* __restrict__ a)
 	{
+		__shared__ uint32_t sh[L * QB_DERIV_THREADS];
+		uint32_t* my = sh + threadIdx.x;
 		const uint32_t n1 = cx.n_max + 1;
 		const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
 		const int t = int(gid / n1);
@@ -40,9 +65,11 @@ namespace qb
 		const int prec = cx.prec;
 		const TableRef tr = tref[t];
 		mpf<L>* at = a + size_t(t) * nk * n1 + n;
-		mpf<L> cur, q;
+		const mpf<L>* pt = pw + size_t(t) * (2 * nk + 1);  // [0] 4^Delta, [1 + k] rho^(q_k), [nk + 1 + k] q_k
+		uint32_t csk;
+		int32_t cexp;
 		{
-			const mpf<L>& c4 = pw[size_t(t) * (nk + 1)];
+			mpf<L> cur;
 			if (tr.job1 >= 0)
 			{
 				// divergent operator: average of the two shifted series               (hor_recursion.cpp:23-27)
@@ -51,30 +78,39 @@ namespace qb
 				copy(v, b[size_t(tr.job1) * n1 + n]);
 				add(u, u, v, prec);
 				mul_2si(u, u, -1);
-				fast::mul(cur, u, c4, prec);
+				fast::mul(cur, u, pt[0], prec);
 			}
 			else
-				fast::mul(cur, b[size_t(tr.job0) * n1 + n], c4, prec);
+				fast::mul(cur, b[size_t(tr.job0) * n1 + n], pt[0], prec);
+			copy(at[0], cur);
+			chain_store(my, csk, cexp, cur);
 		}
-		copy(at[0], cur);
-		copy(q, delta[t]);
+		QB_ROLL
 		for (int k = 1; k < nk; ++k)
 		{
 			mpf<L> f, nxt;
-			fast::add_small(f, q, int64_t(n), prec);   // q_{k-1} + n
-			fast::mul(nxt, cur, f, prec);
+			fast::add_small(f, pt[nk + k], int64_t(n), prec);   // q_{k-1} + n
+			if ((csk & 3u) == K_REG && (f.sk & 3u) == K_REG)
+				fast::mul_strided<L, QB_DERIV_THREADS>(nxt, csk, cexp, my, f, prec);
+			else
+			{
+				mpf<L> cur;
+				chain_load(cur, my, csk, cexp);
+				mul(nxt, cur, f, prec);
+			}
 			copy(at[size_t(k) * n1], nxt);
-			copy(cur, nxt);
-			fast::add_small(q, q, -1, prec);           // pow_ -= 1 (real_function.hpp:239)
+			chain_store(my, csk, cexp, nxt);
 		}
 	}
 
 	// rho-derivative stage, part 2: Horner sums s_k = sum_n a_k[n] rho^n (approximate, real_function.hpp:248-259) and
 	// f_k = s_k * rho^(q_k) / k! (real_function.hpp:262, hor_recursion.cpp:46-53).  One thread per (table, k).
 	template <int L>
-	__global__ void __launch_bounds__(128, 4)
+	__global__ void __launch_bounds__(QB_DERIV_THREADS, 4)
 	    k_horner(DevCtx cx, int n_tables, const mpf<L>* __restrict__ a, const mpf<L>* __restrict__ pw, mpf<L>* __restrict__ fr)
 	{
+		__shared__ uint32_t sh[L * QB_DERIV_THREADS];
+		uint32_t* my = sh + threadIdx.x;
 		const int nk = int(cx.lambda) + 1;
 		const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
 		const int t = int(gid / nk), k = int(gid % nk);
@@ -82,12 +118,33 @@ namespace qb
 		const uint32_t n1 = cx.n_max + 1;
 		const int prec = cx.prec;
 		const mpf<L>* ak = a + (size_t(t) * nk + k) * n1;
-		mpf<L> rho, s;
+		mpf<L> rho;
 		copy(rho, *reinterpret_cast<const mpf<L>*>(cx.rho));
-		copy(s, ak[cx.n_max]);
-		for (uint32_t n = cx.n_max; n-- > 0;) fast::fma(s, s, rho, ak[n], prec);
-		mpf<L> rp, kf, f;
-		copy(rp, pw[size_t(t) * (nk + 1) + 1 + k]);
+		uint32_t ssk;
+		int32_t sexp;
+		{
+			mpf<L> s;
+			copy(s, ak[cx.n_max]);
+			chain_store(my, ssk, sexp, s);
+		}
+		QB_ROLL
+		for (uint32_t n = cx.n_max; n-- > 0;)
+		{
+			mpf<L> r;
+			const mpf<L>& c = ak[n];
+			bool done = false;
+			if ((ssk & 3u) == K_REG && (c.sk & 3u) == K_REG) done = fast::fma_strided<L, QB_DERIV_THREADS>(r, ssk, sexp, my, rho, c, prec);
+			if (!done)
+			{
+				mpf<L> s;
+				chain_load(s, my, ssk, sexp);
+				fma(r, s, rho, c, prec);
+			}
+			chain_store(my, ssk, sexp, r);
+		}
+		mpf<L> s, rp, kf, f;
+		chain_load(s, my, ssk, sexp);
+		copy(rp, pw[size_t(t) * (2 * nk + 1) + 1 + k]);
 		copy(kf, reinterpret_cast<const mpf<L>*>(cx.kfact)[k]);
 		deriv_finish(f, s, rp, kf, uint32_t(k), prec);
 		copy(fr[size_t(t) * nk + k], f);

@@ -22,7 +22,8 @@ namespace qb
 {
 
 	// Powers of one table: pw[t][0] = 4^Delta (src/hor_recursion.cpp:43), pw[t][1 + k] = rho^(q_k) with q_k = Delta - k by
-	// k rounded decrements (include/qboot/algebra/real_function.hpp:239,262).  One thread per table: two exponentials
+	// k rounded decrements (include/qboot/algebra/real_function.hpp:239,262), and the q_k themselves in
+	// pw[t][lambda + 2 + k] (k_scale multiplies by q_{k-1} + n).  Row length 2 (lambda + 1) + 1.  One thread per table: two exponentials
 	// in the extended format (4^Delta and X = rho^(q_0)), then for every k
 	//     rho^(q_k) = X * rho^-k * (1 + eta_k ln rho),   eta_k = q_k - (q_0 - k)   (|eta_k| <~ k 2^-prec |q|, eta^2 negligible)
 	// with rho^-k precomputed in the extended format (DevCtx::rhoinv): 3 extended products per power instead of an exp.
@@ -32,12 +33,14 @@ namespace qb
 		constexpr int E = L + QB_EXT_LIMBS;
 		const int pe = 32 * E;
 		const int np = int(cx.lambda) + 2;
+		const int row = 2 * int(cx.lambda) + 3;
 		int t = blockIdx.x * blockDim.x + threadIdx.x;
 		if (t >= n_tables) return;
 		mpf<L> q0, q, r;
 		copy(q0, delta[t]);
+		copy(pw[size_t(t) * row + np], q0);
 		pow_from_log<L>(r, *reinterpret_cast<const mpf<E>*>(cx.ln4e), q0, *reinterpret_cast<const mpf<E>*>(cx.ln2e), cx.prec);
-		copy(pw[size_t(t) * np], r);
+		copy(pw[size_t(t) * row], r);
 		// X = exp(q0 ln rho) in the extended format
 		mpf<E> X, lnr, l2, qe, te, corr, one, v;
 		copy(lnr, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe));
@@ -46,13 +49,14 @@ namespace qb
 		fast::mul(te, qe, lnr, pe);
 		exp_ext(X, te, l2);
 		narrow(r, X, cx.prec);
-		copy(pw[size_t(t) * np + 1], r);
+		copy(pw[size_t(t) * row + 1], r);
 		set_si(one, 1, pe);
 		copy(q, q0);
 		const mpf<E>* rinv = reinterpret_cast<const mpf<E>*>(cx.rhoinv);
 		for (int k = 1; k + 1 < np; ++k)
 		{
 			add_si(q, q, -1, cx.prec);                 // q_k, rounded as the reference rounds it
+			copy(pw[size_t(t) * row + np + k], q);
 			// eta = q_k - q_0 + k, exact in the extended format
 			mpf<E> qk, eta;
 			widen(qk, q);
@@ -66,7 +70,7 @@ namespace qb
 				fast::mul(v, v, corr, pe);
 			}
 			narrow(r, v, cx.prec);
-			copy(pw[size_t(t) * np + 1 + k], r);
+			copy(pw[size_t(t) * row + 1 + k], r);
 		}
 	}
 
