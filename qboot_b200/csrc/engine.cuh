@@ -115,7 +115,7 @@ namespace qb
 		int hi_priority = 0;
 		std::vector<int> job_of_table;  // first job of every table (+ sentinel)
 		std::vector<int> chunk_t;       // table boundaries of the chunks
-		int n_chunks = 1, timed_chunks = 0;
+		int n_chunks = 1, timed_chunks = 0, sm_count = 0;
 		size_t a_slot_records = 0;      // records of the scaled-coefficient scratch (largest chunk)
 
 		Engine(int dev, int prec_bits)
@@ -328,12 +328,28 @@ namespace qb
 			n_jobs = int(jd.size());
 			job_of_table.assign(size_t(n) + 1, n_jobs);
 			for (int t = 0; t < n; ++t) job_of_table[size_t(t)] = tr[size_t(t)].job0;
-			// chunks of ~CHUNK tables; the scaled-coefficient scratch is one slot per stream
-			static const int CHUNK = std::getenv("QB_CHUNK") ? std::max(256, std::atoi(std::getenv("QB_CHUNK"))) : 6144;
-			// at most 16 chunks (streams); larger batches get larger chunks
-			n_chunks = n > CHUNK ? std::min(16, (n + CHUNK - 1) / CHUNK) : 1;
-			chunk_t.assign(size_t(n_chunks) + 1, n);
-			for (int c = 0; c < n_chunks; ++c) chunk_t[size_t(c)] = int(int64_t(n) * c / n_chunks);
+			// Chunks of CHUNK tables (the last one shorter); the scaled-coefficient scratch is one chunk-sized slot.
+			// CHUNK is a whole number of k_horner waves (one thread per (table, k), 4 CTAs of 128 threads per SM), three by
+			// default: partial waves leave the wide stream's SMs idle at every kernel boundary (measured: 3 waves 150 k
+			// tables/s, 1.6 waves 138 k, 1 wave 128 k at the north-star size).  The scratch is capped at 24 GB.
+			{
+				static const int env_chunk = std::getenv("QB_CHUNK") ? std::max(256, std::atoi(std::getenv("QB_CHUNK"))) : 0;
+				if (sm_count == 0)
+				{
+					cudaDeviceProp prop;
+					QB_CU(cudaGetDeviceProperties(&prop, device));
+					sm_count = prop.multiProcessorCount;
+				}
+				const int64_t wave = std::max<int64_t>(1, int64_t(sm_count) * 4 * 128 / (int64_t(lambda) + 1));
+				const int64_t per_table = int64_t(sizeof(T)) * (int64_t(lambda) + 1) * (int64_t(n_max) + 1);
+				int64_t chunk = env_chunk ? env_chunk : 3 * wave;
+				const int64_t cap = std::max<int64_t>(256, (int64_t(24) << 30) / per_table);
+				if (chunk > cap) chunk = cap >= wave ? cap / wave * wave : cap;
+				if ((n + chunk - 1) / chunk > 32) chunk = ((int64_t(n) + 31) / 32 + wave - 1) / wave * wave;  // at most 32 chunks
+				n_chunks = n > chunk ? int((n + chunk - 1) / chunk) : 1;
+				chunk_t.assign(size_t(n_chunks) + 1, n);
+				for (int c = 0; c < n_chunks; ++c) chunk_t[size_t(c)] = int(std::min<int64_t>(n, chunk * c));
+			}
 			int max_chunk = 0;
 			for (int c = 0; c < n_chunks; ++c) max_chunk = std::max(max_chunk, chunk_t[size_t(c) + 1] - chunk_t[size_t(c)]);
 			a_slot_records = (size_t(lambda) + 1) * (size_t(n_max) + 1) * size_t(n_chunks > 1 ? max_chunk : n);

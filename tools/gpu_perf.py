@@ -26,5 +26,5 @@ for n in sizes:
     eng.set_timing(False); eng.run(); eng.sync(); t0 = time.time()
     for rep in range(3): eng.run()
     eng.sync(); dt = (time.time() - t0) / 3; eng.set_timing(True)
-    print(f"   untimed (chunked, {os.environ.get('QB_CHUNK','6144')} tables/chunk): {dt*1e3:.1f} ms -> {n/dt:.0f} tables/s, {w/dt/peak*100:.1f}% of IMAD peak", flush=True)
+    print(f"   untimed (chunked, QB_CHUNK={os.environ.get('QB_CHUNK','default')}): {dt*1e3:.1f} ms -> {n/dt:.0f} tables/s, {w/dt/peak*100:.1f}% of IMAD peak", flush=True)
     t0 = time.time(); out = eng.fetch(); print(f"   fetch {time.time()-t0:.2f}s {out.nbytes/1e6:.0f} MB", flush=True)
