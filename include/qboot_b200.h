@@ -70,7 +70,8 @@ int qb_block_dim(const qb_handle* h, int sym);
  *   flatten() order (dy-major, dx-minor, complex_function.hpp:72-81).
  * Unit operators (Delta = 0) and divergent operators (primary_op.hpp:68-77, averaged as in hor_recursion.cpp:21-28)
  * are handled as the reference handles them.
- * Large batches are cut into chunks of 6144 tables; each finished chunk is copied to `out` while the later chunks still
+ * Large batches are cut into chunks (three whole waves of the widest kernel: 11 367 tables at lambda = 19 on a B200);
+ * each finished chunk is copied to `out` while the later chunks still
  * compute (pinned `out` makes that copy truly asynchronous; pageable memory works, more slowly).  Returns after the last
  * copy has landed. */
 int qb_gblock_batch(qb_handle* h, int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S,
