@@ -57,8 +57,11 @@ def raw(path):
     hdr, units, data = rows[0], rows[1], rows[2:]
     ki = hdr.index("Kernel Name")
     seen = collections.OrderedDict()
-    for r in data:
-        seen.setdefault(short(r[ki]), r)  # first captured launch of every kernel
+    gi = hdr.index("launch__grid_size")
+    for r in data:  # the captured launch with the largest grid of every kernel
+        k = short(r[ki])
+        if k not in seen or float(r[gi].replace(",", "")) > float(seen[k][gi].replace(",", "")):
+            seen[k] = r
     order = ["k_rec_coeffs", "k_polyvals", "k_pow", "k_series", "k_scale", "k_horner", "k_rho_to_z", "k_offdiag_val", "k_offdiag_close"]
     names = sorted(seen, key=lambda n: next((i for i, o in enumerate(order) if n.startswith(o)), 99))
     print("metric".ljust(46) + "".join(n[:17].rjust(18) for n in names))
