@@ -107,10 +107,10 @@ namespace qb
 		T *j_delta = nullptr, *j_S = nullptr, *j_P = nullptr, *j_b0 = nullptr;
 		uint32_t* j_spin = nullptr;
 		std::vector<cudaEvent_t> ev;    // 5 per chunk when timing
-		cudaStream_t lo_stream = nullptr;        // wide kernels of all chunks
+		cudaStream_t lo_stream = nullptr, mid_stream = nullptr, fin_stream = nullptr;  // wide kernels of all chunks, by stage
 		std::vector<cudaStream_t> hi_streams;    // latency-bound kernels, one stream per chunk
 		std::vector<cudaEvent_t> dep_ev;         // 4 per chunk
-		cudaEvent_t fork_ev = nullptr, copy_done_ev = nullptr;
+		cudaEvent_t fork_ev = nullptr, copy_done_ev = nullptr, fin_done_ev = nullptr, lo_done_ev = nullptr;
 		cudaStream_t copy_stream = nullptr;      // device -> host copies of finished chunks (fetch_dst)
 		int hi_priority = 0;
 		std::vector<int> job_of_table;  // first job of every table (+ sentinel)
@@ -131,7 +131,8 @@ namespace qb
 			                  &d_fb_terms})
 				b->release();
 			for (cudaStream_t s : hi_streams) cudaStreamDestroy(s);
-			if (lo_stream) cudaStreamDestroy(lo_stream);
+			for (cudaStream_t s_ : {lo_stream, mid_stream, fin_stream, copy_stream})
+				if (s_) cudaStreamDestroy(s_);
 			if (stream) cudaStreamDestroy(stream);
 		}
 		// QB_DEBUG_SYNC=1: synchronise after every kernel so that a fault is attributed to the kernel that raised it
@@ -496,8 +497,12 @@ namespace qb
 				int pr_lo = 0, pr_hi = 0;
 				QB_CU(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
 				QB_CU(cudaStreamCreateWithPriority(&lo_stream, cudaStreamNonBlocking, pr_lo));
+				QB_CU(cudaStreamCreateWithPriority(&mid_stream, cudaStreamNonBlocking, pr_lo));
+				QB_CU(cudaStreamCreateWithPriority(&fin_stream, cudaStreamNonBlocking, pr_lo));
 				QB_CU(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
 				QB_CU(cudaEventCreateWithFlags(&copy_done_ev, cudaEventDisableTiming));
+				QB_CU(cudaEventCreateWithFlags(&fin_done_ev, cudaEventDisableTiming));
+				QB_CU(cudaEventCreateWithFlags(&lo_done_ev, cudaEventDisableTiming));
 				QB_CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
 				hi_priority = pr_hi;
 			}
@@ -514,8 +519,13 @@ namespace qb
 				}
 			}
 			auto EV = [&](int c, int i) { return dep_ev[size_t(4 * c + i)]; };  // 0 poly done, 1 series done, 2 horner done, 3 finish done
+			// Three low-priority streams for the wide stages, so that their kernels fill each other's tails and stalls:
+			//   lo_stream   coefficients + polynomial values of every chunk, in order
+			//   mid_stream  scale + Horner of every chunk, in order (they share the one `a` scratch slot)
+			//   fin_stream  rho -> z + transverse recursion (instruction-fetch-bound, low issue rate) and the copy-out
+			// plus one high-priority stream per chunk for the latency-bound powers and series recurrence.
 			QB_CU(cudaEventRecord(fork_ev, stream));
-			QB_CU(cudaStreamWaitEvent(lo_stream, fork_ev, 0));
+			for (cudaStream_t s_ : {lo_stream, mid_stream, fin_stream}) QB_CU(cudaStreamWaitEvent(s_, fork_ev, 0));
 			for (int c = 0; c < n_chunks; ++c) QB_CU(cudaStreamWaitEvent(hi_streams[size_t(c)], fork_ev, 0));
 			for (int c = 0; c < n_chunks; ++c)
 			{
@@ -532,18 +542,23 @@ namespace qb
 			for (int c = 0; c < n_chunks; ++c)
 			{
 				const Range r = range_of(c);
-				QB_CU(cudaStreamWaitEvent(lo_stream, EV(c, 1), 0));
-				stage_deriv(r, lo_stream);
-				stage_finish(r, lo_stream);  // wide per-level kernels: same stream as the other wide stages
+				QB_CU(cudaStreamWaitEvent(mid_stream, EV(c, 1), 0));
+				stage_deriv(r, mid_stream);
+				QB_CU(cudaEventRecord(EV(c, 2), mid_stream));
+				QB_CU(cudaStreamWaitEvent(fin_stream, EV(c, 2), 0));
+				stage_finish(r, fin_stream);
 				if (fetch_dst)
 				{
-					QB_CU(cudaEventRecord(EV(c, 3), lo_stream));
+					QB_CU(cudaEventRecord(EV(c, 3), fin_stream));
 					QB_CU(cudaStreamWaitEvent(copy_stream, EV(c, 3), 0));
 					if (int rc_ = copy_chunk_out(r, copy_stream)) return rc_;
 				}
 			}
-			QB_CU(cudaEventRecord(EV(0, 2), lo_stream));
-			QB_CU(cudaStreamWaitEvent(stream, EV(0, 2), 0));
+			// join: fin_stream is behind mid_stream, which is behind every series stream; lo_stream is behind nothing
+			QB_CU(cudaEventRecord(fin_done_ev, fin_stream));
+			QB_CU(cudaStreamWaitEvent(stream, fin_done_ev, 0));
+			QB_CU(cudaEventRecord(lo_done_ev, lo_stream));
+			QB_CU(cudaStreamWaitEvent(stream, lo_done_ev, 0));
 			if (fetch_dst)
 			{
 				QB_CU(cudaEventRecord(copy_done_ev, copy_stream));
