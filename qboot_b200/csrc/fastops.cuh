@@ -329,164 +329,20 @@ namespace qb
 			if constexpr (S + 1 < PL::NSEG) mul_short_seg<L, S + 1, AS>(EV, OD, b, a, n0, n1, g);
 		}
 
-		// Four rows per iteration (used when the padded limb count is a multiple of 4): the window slides by four limbs, so
-		// the fold / retire work and the loop overhead are paid once per four rows, and the iteration carries seven
-		// independent carry chains instead of three (more instruction-level parallelism for the few resident warps).
-		//   EV[m] <-> position i + m (even m pairs),  OD[m] <-> position i + 1 + m (even m pairs); rows r = 0..3, kk even:
-		//   r0: EV[kk]   += a0 b[kk]     OD[kk]   =  a0 b[kk+1] (fresh)
-		//   r1: OD[kk]   += a1 b[kk]     EV[kk+2] += a1 b[kk+1]
-		//   r2: EV[kk+2] += a2 b[kk]     OD[kk+2] += a2 b[kk+1]
-		//   r3: OD[kk+2] += a3 b[kk]     EV[kk+4] += a3 b[kk+1]
-		// Carry tails: every accumulator stays below B^(LP+5) (window value < B^LP at the top of the iteration, row r adds
-		// < B^(LP+1+r)), and each chain is propagated as far as its own bound allows (see the comments at the chains).
-		template <int L>
-		struct ShortPlan4 : ShortPlan<L>
-		{
-			using P = ShortPlan<L>;
-			static constexpr int jlo(int s)
-			{
-				return (P::retire(s) || P::abs_low(s) - (P::i1(s) - 4) <= 0) ? 0 : ((P::abs_low(s) - (P::i1(s) - 4)) & ~1);
-			}
-		};
-
-		template <int L, int S, int AS>
-		QB_HD QB_INLINE void mul_short_seg4(uint32_t (&EV)[((L + 1) & ~1) + 6], uint32_t (&OD)[((L + 1) & ~1) + 4], const uint32_t (&b)[(L + 1) & ~1],
-		                                    const uint32_t* a, uint32_t (&nx)[4], uint32_t (&g)[6])
-		{
-			using PL = ShortPlan4<L>;
-			constexpr int LP = PL::LP, i0 = PL::i0(S), i1 = PL::i1(S), kmin = PL::kmin(S), jlo = PL::jlo(S);
-			constexpr bool retire = PL::retire(S);
-			constexpr int ms = jlo >= 4 ? jlo - 4 : 0;  // first window entry the fold has to produce
-			static_assert(LP % 4 == 0 && (i1 - i0) % 4 == 0 && kmin % 2 == 0 && jlo % 2 == 0 && (!retire || kmin == 0) && jlo <= kmin,
-			              "short-product staircase (4 rows)");
-#pragma unroll 1
-			for (int i = i0; i < i1; i += 4)
-			{
-				const uint32_t a0 = nx[0], a1 = nx[1], a2 = nx[2], a3 = nx[3];
-				if (i + 4 < LP)
-				{
-#pragma unroll
-					for (int r = 0; r < 4; ++r) nx[r] = (i + 4 + r < L) ? a[(i + 4 + r) * AS] : 0u;
-				}
-				QB_CY_DECL
-				// r0 even: EV < B^LP + B^(LP+1)
-				QB_MAD_FIRST(EV[kmin], EV[kmin + 1], a0, b[kmin]);
-#pragma unroll
-				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(EV[k], EV[k + 1], a0, b[k]);
-				QB_ADDC_CC(EV[LP]);
-				QB_ADDC_END(EV[LP + 1]);
-				// r0 odd: OD fresh
-#pragma unroll
-				for (int k = kmin; k < LP; k += 2)
-				{
-					uint64_t t = uint64_t(a0) * uint64_t(b[k + 1]);
-					OD[k] = uint32_t(t);
-					OD[k + 1] = uint32_t(t >> 32);
-				}
-				OD[LP] = 0u;
-				OD[LP + 1] = 0u;
-				OD[LP + 2] = 0u;
-				OD[LP + 3] = 0u;
-				// r1 even: OD < 2 B^(LP+1)
-				QB_MAD_FIRST(OD[kmin], OD[kmin + 1], a1, b[kmin]);
-#pragma unroll
-				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(OD[k], OD[k + 1], a1, b[k]);
-				QB_ADDC_END(OD[LP]);
-				// r1 odd: EV < B^(LP+3)
-				QB_MAD_FIRST(EV[kmin + 2], EV[kmin + 3], a1, b[kmin + 1]);
-#pragma unroll
-				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(EV[k + 2], EV[k + 3], a1, b[k + 1]);
-				QB_ADDC_CC(EV[LP + 2]);
-				QB_ADDC_END(EV[LP + 3]);
-				// r2 even: EV < B^(LP+4)
-				QB_MAD_FIRST(EV[kmin + 2], EV[kmin + 3], a2, b[kmin]);
-#pragma unroll
-				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(EV[k + 2], EV[k + 3], a2, b[k]);
-				QB_ADDC_CC(EV[LP + 2]);
-				QB_ADDC_END(EV[LP + 3]);
-				// r2 odd: OD < B^(LP+3)
-				QB_MAD_FIRST(OD[kmin + 2], OD[kmin + 3], a2, b[kmin + 1]);
-#pragma unroll
-				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(OD[k + 2], OD[k + 3], a2, b[k + 1]);
-				QB_ADDC_END(OD[LP + 2]);
-				// r3 even: OD < B^(LP+4)
-				QB_MAD_FIRST(OD[kmin + 2], OD[kmin + 3], a3, b[kmin]);
-#pragma unroll
-				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(OD[k + 2], OD[k + 3], a3, b[k]);
-				QB_ADDC_CC(OD[LP + 2]);
-				QB_ADDC_END(OD[LP + 3]);
-				// r3 odd: EV < B^(LP+5)
-				QB_MAD_FIRST(EV[kmin + 4], EV[kmin + 5], a3, b[kmin + 1]);
-#pragma unroll
-				for (int k = kmin + 2; k < LP; k += 2) QB_MAD_NEXT(EV[k + 4], EV[k + 5], a3, b[k + 1]);
-				QB_ADDC_CC(EV[LP + 4]);
-				QB_ADDC_END(EV[LP + 5]);
-				// fold OD into EV and slide the window by four limbs; positions i .. i+3 leave the window
-#define QB_OD_AT(j) (((j) >= kmin && (j) < LP + 4) ? OD[(j)] : 0u)
-				if (retire)
-				{
-					g[4] = g[2];
-					g[5] = g[3];
-					g[0] = EV[0];
-					QB_ADD_FIRST(g[1], EV[1], OD[0]);
-					QB_ADD_NEXT(g[2], EV[2], OD[1]);
-					QB_ADD_NEXT(g[3], EV[3], OD[2]);
-#pragma unroll
-					for (int m = 0; m < LP + 2; ++m) QB_ADD_NEXT(EV[m], EV[m + 4], QB_OD_AT(m + 3));
-				}
-				else if (ms == 0)
-				{
-					// positions i .. i+3 are below everything that is read later, but their carry is kept
-					uint32_t dump;
-					QB_ADD_FIRST(dump, EV[1], QB_OD_AT(0));
-					QB_ADD_NEXT(dump, EV[2], QB_OD_AT(1));
-					QB_ADD_NEXT(dump, EV[3], QB_OD_AT(2));
-					(void)dump;
-#pragma unroll
-					for (int m = 0; m < LP + 2; ++m) QB_ADD_NEXT(EV[m], EV[m + 4], QB_OD_AT(m + 3));
-				}
-				else
-				{
-					// entries below jlo are zero (and OD below kmin >= jlo is not written in this segment)
-					QB_ADD_FIRST(EV[ms], EV[ms + 4], QB_OD_AT(ms + 3));
-#pragma unroll
-					for (int m = ms + 1; m < LP + 2; ++m) QB_ADD_NEXT(EV[m], EV[m + 4], QB_OD_AT(m + 3));
-				}
-#undef QB_OD_AT
-				EV[LP + 2] = 0u;
-				EV[LP + 3] = 0u;
-				EV[LP + 4] = 0u;
-				EV[LP + 5] = 0u;
-			}
-			if constexpr (S + 1 < PL::NSEG) mul_short_seg4<L, S + 1, AS>(EV, OD, b, a, nx, g);
-		}
-
 		template <int L, int AS = 1>
 		QB_HD QB_INLINE bool mul_top_short(uint32_t* X, uint32_t& st, const uint32_t* a, const uint32_t* rb)
 		{
 			constexpr int LP = (L + 1) & ~1;  // even
-			constexpr bool FOUR = (LP % 4 == 0) && (LP >= 8);
-			uint32_t b[LP], EV[LP + (FOUR ? 6 : 4)], OD[LP + (FOUR ? 4 : 2)];
+			uint32_t b[LP], EV[LP + 4], OD[LP + 2];
 #pragma unroll
 			for (int j = 0; j < LP; ++j) b[j] = j < L ? rb[j] : 0u;
 #pragma unroll
-			for (int j = 0; j < LP + (FOUR ? 6 : 4); ++j) EV[j] = 0u;
+			for (int j = 0; j < LP + 4; ++j) EV[j] = 0u;
 #pragma unroll
-			for (int j = 0; j < LP + (FOUR ? 4 : 2); ++j) OD[j] = 0u;
-			// g[0..3]: the four positions below the window; g[4], g[5]: the two below those
-			uint32_t g[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-			if constexpr (FOUR)
-			{
-				uint32_t nx[4];
-#pragma unroll
-				for (int r = 0; r < 4; ++r) nx[r] = (r < L) ? a[r * AS] : 0u;
-				mul_short_seg4<L, 0, AS>(EV, OD, b, a, nx, g);
-			}
-			else
-			{
-				uint32_t n0 = a[0], n1 = (1 < L) ? a[AS] : 0u;
-				mul_short_seg<L, 0, AS>(EV, OD, b, a, n0, n1, g);
-			}
+			for (int j = 0; j < LP + 2; ++j) OD[j] = 0u;
+			uint32_t g[6] = {0u, 0u, 0u, 0u, 0u, 0u};  // g[0..3]: the four positions below the window; g[4], g[5]: the two below those
+			uint32_t n0 = a[0], n1 = (1 < L) ? a[AS] : 0u;
+			mul_short_seg<L, 0, AS>(EV, OD, b, a, n0, n1, g);
 			uint32_t f4, f5;
 			if (L % 2 == 0)
 			{
