@@ -13,9 +13,11 @@ of the grid, there is no data-path collective; rank 0 gathers the timings).
   value     tables/s with the inputs already resident in HBM (qb_gblock_plan done; qb_gblock_run timed with CUDA
             events on the launching stream; barrier + synchronize on both sides; max over ranks)
   e2e       tables/s through qb_gblock_batch with HOST buffers in and out (planning, H2D, kernels, D2H all timed)
-  roofline  the dominant kernel (rho-derivative chains) against the MEASURED integer multiply-add rate of this GPU
-            (qb_imad_peak); the path is IMAD-bound (>= 350 MAC per HBM byte), so the bound is "imad", not hbm/tensor
+  roofline  the dominant stage (rho-derivative chains: k_scale + k_horner) against the MEASURED limb-product rate of
+            this GPU (qb_imad_peak, IMAD.WIDE.U32); the path is multiply-bound (>= 8 MAC per HBM byte against a machine
+            balance of ~1), so the bound is "imad", not hbm/tensor; `traffic` = ncu dram bytes of that stage per launch
   cpu_baseline  oracle/_ref (the unmodified reference, MPFR) on this box's host cores, bounded sample, rank 0, N = 1
+  parity_check  (with cpu_baseline, untimed) 64 tables of the end-to-end leg's output against the reference, word for word
 """
 from __future__ import annotations
 
@@ -290,6 +292,12 @@ def main():
                 t = ref.time_gblock(PREC, N_MAX, LAM, DIM, delta[:sample], spin[:sample], S[:sample], P[:sample], cores)
                 line["cpu_baseline"] = {"value": sample / t, "unit": UNIT, "cores": cores, "kind": "reference",
                                         "sample": f"first {sample} tables of the same workload through the unmodified reference (qboot::gBlock, MPFR 4.2.1) on {cores} host threads"}
+                # not timed: the tables the end-to-end leg just wrote to host memory, against the reference's, word for word
+                idx = np.arange(0, n, max(1, n // 64))[:64]
+                want = ref.gblock(PREC, N_MAX, LAM, DIM, delta[idx], spin[idx], S[idx], P[idx])
+                got = h_out.numpy().view(np.uint32)[idx]
+                line["parity_check"] = {"tables": int(len(idx)), "bit_identical": bool(np.array_equal(got, want)),
+                                        "against": "unmodified reference (oracle/_ref) on the same keys"}
         except Exception as ex:  # the baseline is reported, never required
             line["cpu_baseline"] = {"error": str(ex)}
     print(json.dumps(line))

@@ -222,3 +222,19 @@ def test_chunked_streams_match_single_chunk(tmp_path):
     assert int(out["launches"]) > 2 * 6 * 5  # several chunks really ran
     assert np.array_equal(out["g"], want)
     assert np.array_equal(out["g2"], want)
+
+
+def test_bench_workload_vs_reference(ref):
+    """The benchmark's own workload (mixed-Ising key set at lambda = 19, n_Max = 400, 1024-bit, full-width sample points)
+    sampled across spins and (S, P) classes, against the reference run on this box: what bench.py times is what is pinned."""
+    from qboot_b200 import workload as wl
+
+    prec, n_max, lam = 1024, 400, 19
+    keys = wl.sweep_keys(prec, lam, 20, 50, 49096)[::613]
+    spin, delta, S, P = wl.to_records(keys, prec)
+    eng = _engine(prec, n_max, lam)
+    got = eng.gblock(spin, delta, S, P)
+    eng.close()
+    want = ref.gblock(prec, n_max, lam, "3", delta, spin, S, P)
+    bad = [i for i in range(len(keys)) if not np.array_equal(got[i], want[i])]
+    assert len(keys) >= 80 and not bad, bad
