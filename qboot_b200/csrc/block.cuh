@@ -72,6 +72,18 @@ namespace qb
 		{
 			copy(xv, x[int64_t(j) * xstride]);
 			copy(mv, M[j * (lambda + 1) + i]);
+			if (is_zero(mv) && kind(xv) == K_REG)
+			{
+				// The matrix is triangular and the reference multiplies through its zeros: x * 0 = +-0 exactly, and adding
+				// a zero leaves a nonzero z unchanged; zero + zero is -0 only if both are.  Taken inline so that the lanes
+				// of a warp (different columns, different zero patterns) stay converged.
+				if (kind(z) == K_REG) continue;
+				if (is_zero(z))
+				{
+					z.sk &= ~SIGN_BIT | ((xv.sk ^ mv.sk) & SIGN_BIT);
+					continue;
+				}
+			}
 			fast::mul(t, xv, mv, prec);
 			fast::add(z, z, t, prec);
 		}
