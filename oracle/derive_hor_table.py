@@ -156,7 +156,7 @@ def main():
     with open(os.path.join(root, "oracle", "hor_table.json"), "w") as f:
         json.dump(families, f, separators=(",", ":"))
     # C tables
-    lines = ["// GENERATED by tools/derive_hor_table.py -- do not edit.",
+    lines = ["// GENERATED by oracle/derive_hor_table.py -- do not edit.",
              "// Integer coefficient tensors of the HOR series recurrence, recovered by exact interpolation.",
              "// mono = {coef, eDelta, eS, eP, espin, eeps}; poly = {first mono, #monos, constant term, flag}",
              "// flag 1: the stored polynomial is to be multiplied by (3 - 2 Delta + 2 eps).",

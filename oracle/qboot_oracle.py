@@ -7,7 +7,7 @@ What is restated (reference v0.8.1, paths relative to /root/reference):
     result rounded once to nearest-even at `prec` bits (MPFR_RNDN, src/mp/real.cpp:5-6).  Class `R` below does that with
     exact Python integers; pow/exp go through mpmath at prec + 256 bits and are rounded once.
   * _get_rec_coeffs (include/qboot/hor_formula.hpp:34-39, src/hor_formula.cpp) from the integer tensors of
-    oracle/hor_table.json (recovered by exact interpolation, tools/derive_hor_table.py), evaluated monomial by monomial
+    oracle/hor_table.json (recovered by exact interpolation, oracle/derive_hor_table.py), evaluated monomial by monomial
     in lexicographic order -- the order that reproduces the reference bit for bit;
   * hBlock_shifted incl. unit and divergent operators (src/hor_recursion.cpp:14-39, include/qboot/primary_op.hpp:53-77);
   * gBlock_real (src/hor_recursion.cpp:40-56, include/qboot/algebra/real_function.hpp:236-264);

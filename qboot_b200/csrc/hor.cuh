@@ -4,7 +4,7 @@
 //                  src/hor_formula.cpp:8-296 spin 0, :298-2055 spin > 0)
 //   series       : b[n] = -(sum_{i=1}^{min(n,K-1)} p_i(n) b[n-i]) / p_0(n)   (src/hor_recursion.cpp:31-37)
 //
-// The middle polynomials p_1..p_{K-2} come from the integer tensors in hor_table.inc (tools/derive_hor_table.py);
+// The middle polynomials p_1..p_{K-2} come from the integer tensors in hor_table.inc (oracle/derive_hor_table.py);
 // each coefficient is evaluated monomial by monomial in lexicographic order, every product and every partial sum
 // rounded at `prec` bits, which reproduces the reference's MPFR evaluation bit for bit.
 //

@@ -2,7 +2,7 @@
 """GPU check of the register-resident fast paths (PTX carry chains) against MPFR through oracle/_ref."""
 import os, sys, random
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import qboot_b200 as qb
 from oracle import ref
 from tests.golden.make_golden import rnd_num

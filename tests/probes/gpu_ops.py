@@ -2,7 +2,7 @@
 """GPU primitive check (development aid): device build of each mpf routine vs MPFR through oracle/_ref."""
 import os, sys, random
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import qboot_b200 as qb
 from oracle import ref
 
