@@ -11,8 +11,7 @@
 //                      ComplexFunction mul / proj, include/qboot/algebra/complex_function.hpp:190-206)
 //
 // Every function performs the reference's operations in the reference's order, each rounded at `prec` bits.
-// Staging rule as in hor.cuh: arithmetic only on thread-local records; tables in global memory are read with copy()
-// into locals and written with copy() from locals.
+// Operand placement as in hor.cuh: anywhere; the functions say where their results go.
 #pragma once
 
 #include "hor.cuh"

@@ -3,7 +3,7 @@
 // Same contract as mpf.cuh (exact result, rounded once to nearest-even at `prec` bits) and bit-identical results; the
 // difference is where the limbs live.  The generic routines of mpf.cuh build the exact 2L-limb intermediate in
 // thread-local arrays and index them dynamically, which on the GPU means stack (local-memory) traffic: the first ncu
-// capture showed k_deriv moving 22 GB through DRAM for 0.2 GB of algorithmic data.  Here every intermediate is a
+// capture showed the first derivative kernel moving 22 GB through DRAM for 0.2 GB of algorithmic data.  Here every intermediate is a
 // statically indexed array that the compiler keeps in registers:
 //
 //   * the L x L product keeps only its top L + 3 limbs and an OR of everything below (`mul_top`): a rolled loop over the

@@ -8,9 +8,9 @@
 // each coefficient is evaluated monomial by monomial in lexicographic order, every product and every partial sum
 // rounded at `prec` bits, which reproduces the reference's MPFR evaluation bit for bit.
 //
-// Staging rule (device): the arithmetic routines of mpf.cuh are only ever handed thread-local records.  Operands that
-// live in global or shared memory are copied into locals first and results are copied out afterwards, so that every
-// limb routine addresses one memory space only.
+// Operands may live in registers, thread-local, shared or global memory: all arithmetic is force-inlined (mpf.cuh), so
+// every limb access compiles to the load of the space the operand really lives in.  The register fast paths of
+// fastops.cuh are used wherever an operation sits on a hot loop; the generic routines of mpf.cuh elsewhere.
 #pragma once
 
 #include "fastops.cuh"

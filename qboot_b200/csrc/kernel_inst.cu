@@ -1,5 +1,5 @@
 // qboot_b200 -- kernel translation unit: nvcc -DQB_L=<limbs> -DQB_KGROUP=<0..4> kernel_inst.cu
-//   group 0: k_rec_coeffs, k_polyvals, k_ops    1: k_series    2: k_scale, k_horner    3: k_finish    4: k_vtod, k_fblock, k_pow
+//   group 0: k_rec_coeffs, k_polyvals, k_ops    1: k_series    2: k_scale, k_horner    3: k_rho_to_z, k_offdiag_val, k_offdiag_close    4: k_vtod, k_fblock, k_pow
 #if !defined(QB_L) || !defined(QB_KGROUP)
 #error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..4>"
 #endif

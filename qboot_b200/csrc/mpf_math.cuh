@@ -108,7 +108,7 @@ namespace qb
 	                        const mpf<L + QB_EXT_LIMBS>& ln2, int prec)
 	{
 		constexpr int E = L + QB_EXT_LIMBS;
-		// lnx / ln2 may live in global memory: stage them into thread-local records (staging rule, hor.cuh)
+		// lnx / ln2 may live in global memory: stage them into thread-local records once, they are reused below
 		mpf<E> ye, t, v, lx, l2;
 		copy(lx, lnx);
 		copy(l2, ln2);
