@@ -109,68 +109,92 @@ namespace qb
 	// One row entry of the recursion: everything except the same-row correction, i.e. val / common_factor.
 	// f is the Mixed table (packed, anywhere), rows n-1 and n-2 must be complete; val, S, P, qc4 thread-local.
 	// (context.cpp:72-121)
+	//
+	// The 36 operations of the entry are run by a small interpreter -- a step counter decoded into (op, dst, src, src2 /
+	// integer) and ONE instance of every primitive -- instead of straight-line code: with all arithmetic force-inlined
+	// the straight-line version was 63 000 instructions (1 MB) per kernel and ran at the speed of instruction fetch
+	// (ncu: 5-10 no-instruction stall cycles per issue).  Operation order and operands are exactly the reference's.
 	template <int L>
 	QB_HD QB_NOINLINE void offdiag_val(mpf<L>& val, const mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& S,
 	                                   const mpf<L>& P, const mpf<L>& qc4, Rational eps, int prec)
 	{
-		mpf<L> term, t2, h;
-#define QB_LOADF(mm, nn) copy(h, f[int64_t(cf_index(lambda, (mm), (nn))) * fs])
-		// h[m + 2, n - 1]
-		QB_LOADF(m + 2, n - 1);
-		fast::mul_small(val, h, -int64_t(m + 1) * (m + 2), prec);
-		// h[m + 1, n - 1]
-		add_q(term, S, eps.num, eps.den, prec);
-		fast::mul_small(term, term, 2, prec);
-		fast::add_small(term, term, -int64_t(m + 4 * n - 6), prec);
-		fast::mul_small(term, term, 2 * (m + 1), prec);
-		QB_LOADF(m + 1, n - 1);
-		fast::mul(term, term, h, prec);
-		fast::add(val, val, term, prec);
-		// h[m, n - 1]
-		set_q(term, eps.num * int64_t(4 * (m + n - 1)), eps.den, prec);
-		fast::add_small(term, term, int64_t(m) * (m + 8 * n - 5) + int64_t(n) * (4 * n - 2) - 2, prec);
-		fast::mul_small(t2, P, 2, prec);
-		fast::add(term, term, t2, prec);
-		fast::mul_small(t2, S, int64_t(8 * n + 4 * m - 8), prec);
-		fast::add(term, term, t2, prec);
-		fast::add(term, term, qc4, prec);
-		fast::mul_small(term, term, 4, prec);
-		QB_LOADF(m, n - 1);
-		fast::mul(term, term, h, prec);
-		fast::add(val, val, term, prec);
-		// h[m - 1, n - 1]
-		if (m >= 1)
+		enum : int { VAL = 0, TERM = 1, T2 = 2, H = 3, RS = 4, RP = 5, RQ = 6 };
+		enum : int { LOADF, MULS, ADDS, ADD, MUL, SETQ, ADDQ, DIVQ, NOP };
+		mpf<L> R[7];
+		copy(R[RS], S);
+		copy(R[RP], P);
+		copy(R[RQ], qc4);
+		const int64_t M = m, N = n, en = eps.num;
+		QB_ROLL
+		for (int step = 0; step < 41; ++step)
 		{
-			set_q(term, eps.num * int64_t(2 * (m + 1 - 2 * n)), eps.den, prec);
-			fast::add_small(term, term, int64_t(m) * (m + 12 * n - 13) + int64_t(n) * (12 * n - 34) + 22, prec);
-			fast::mul_small(t2, P, 2, prec);
-			fast::add(term, term, t2, prec);
-			fast::mul_small(t2, S, int64_t(8 * n + 2 * m - 10), prec);
-			fast::add(term, term, t2, prec);
-			fast::mul_small(term, term, 8, prec);
-			QB_LOADF(m - 1, n - 1);
-			fast::mul(term, term, h, prec);
-			fast::add(val, val, term, prec);
+			int op = NOP, d = 0, a = 0, b = 0;
+			int64_t v = 0;
+			switch (step)
+			{
+			// h[m + 2, n - 1]
+			case 0: op = LOADF; v = cf_index(lambda, m + 2, n - 1); break;
+			case 1: op = MULS; d = VAL; a = H; v = -(M + 1) * (M + 2); break;
+			// h[m + 1, n - 1]
+			case 2: op = ADDQ; d = TERM; a = RS; v = en; break;
+			case 3: op = MULS; d = TERM; a = TERM; v = 2; break;
+			case 4: op = ADDS; d = TERM; a = TERM; v = -(M + 4 * N - 6); break;
+			case 5: op = MULS; d = TERM; a = TERM; v = 2 * (M + 1); break;
+			case 6: op = LOADF; v = cf_index(lambda, m + 1, n - 1); break;
+			case 7: op = MUL; d = TERM; a = TERM; b = H; break;
+			case 8: op = ADD; d = VAL; a = VAL; b = TERM; break;
+			// h[m, n - 1]
+			case 9: op = SETQ; d = TERM; v = en * (4 * (M + N - 1)); break;
+			case 10: op = ADDS; d = TERM; a = TERM; v = M * (M + 8 * N - 5) + N * (4 * N - 2) - 2; break;
+			case 11: op = MULS; d = T2; a = RP; v = 2; break;
+			case 12: op = ADD; d = TERM; a = TERM; b = T2; break;
+			case 13: op = MULS; d = T2; a = RS; v = 8 * N + 4 * M - 8; break;
+			case 14: op = ADD; d = TERM; a = TERM; b = T2; break;
+			case 15: op = ADD; d = TERM; a = TERM; b = RQ; break;
+			case 16: op = MULS; d = TERM; a = TERM; v = 4; break;
+			case 17: op = LOADF; v = cf_index(lambda, m, n - 1); break;
+			case 18: op = MUL; d = TERM; a = TERM; b = H; break;
+			case 19: op = ADD; d = VAL; a = VAL; b = TERM; break;
+			// h[m - 1, n - 1]
+			case 20: if (m >= 1) { op = SETQ; d = TERM; v = en * (2 * (M + 1 - 2 * N)); } break;
+			case 21: if (m >= 1) { op = ADDS; d = TERM; a = TERM; v = M * (M + 12 * N - 13) + N * (12 * N - 34) + 22; } break;
+			case 22: if (m >= 1) { op = MULS; d = T2; a = RP; v = 2; } break;
+			case 23: if (m >= 1) { op = ADD; d = TERM; a = TERM; b = T2; } break;
+			case 24: if (m >= 1) { op = MULS; d = T2; a = RS; v = 8 * N + 2 * M - 10; } break;
+			case 25: if (m >= 1) { op = ADD; d = TERM; a = TERM; b = T2; } break;
+			case 26: if (m >= 1) { op = MULS; d = TERM; a = TERM; v = 8; } break;
+			case 27: if (m >= 1) { op = LOADF; v = cf_index(lambda, m - 1, n - 1); } break;
+			case 28: if (m >= 1) { op = MUL; d = TERM; a = TERM; b = H; } break;
+			case 29: if (m >= 1) { op = ADD; d = VAL; a = VAL; b = TERM; } break;
+			// h[m + 1, n - 2] and h[m + 2, n - 2]
+			case 30: if (n >= 2) { op = SETQ; d = TERM; v = -2 * en; } break;
+			case 31: if (n >= 2) { op = ADDS; d = TERM; a = TERM; v = 3 * M + 4 * N - 6; } break;
+			case 32: if (n >= 2) { op = MULS; d = T2; a = RS; v = 2; } break;
+			case 33: if (n >= 2) { op = ADD; d = TERM; a = TERM; b = T2; } break;
+			case 34: if (n >= 2) { op = MULS; d = TERM; a = TERM; v = 8 * (M + 1); } break;
+			case 35: if (n >= 2) { op = LOADF; v = cf_index(lambda, m + 1, n - 2); } break;
+			case 36: if (n >= 2) { op = MUL; d = TERM; a = TERM; b = H; } break;
+			case 37: if (n >= 2) { op = LOADF; v = cf_index(lambda, m + 2, n - 2); } break;
+			case 38: if (n >= 2) { op = MULS; d = T2; a = H; v = 4 * (M + 1) * (M + 2); } break;
+			case 39: if (n >= 2) { op = ADD; d = TERM; a = TERM; b = T2; } break;
+			case 40: if (n >= 2) { op = ADD; d = VAL; a = VAL; b = TERM; } break;
+			default: break;
+			}
+			switch (op)
+			{
+			case LOADF: copy(R[H], f[v * fs]); break;
+			case MULS: fast::mul_small(R[d], R[a], v, prec); break;
+			case ADDS: fast::add_small(R[d], R[a], v, prec); break;
+			case ADD: fast::add(R[d], R[a], R[b], prec); break;
+			case MUL: fast::mul(R[d], R[a], R[b], prec); break;
+			case SETQ: set_q(R[d], v, eps.den, prec); break;
+			case ADDQ: add_q(R[d], R[a], v, eps.den, prec); break;
+			default: break;
+			}
 		}
-		// h[m + 1, n - 2] and h[m + 2, n - 2]
-		if (n >= 2)
-		{
-			set_q(term, -2 * eps.num, eps.den, prec);
-			fast::add_small(term, term, int64_t(3 * m + 4 * n - 6), prec);
-			fast::mul_small(t2, S, 2, prec);
-			fast::add(term, term, t2, prec);
-			fast::mul_small(term, term, int64_t(8 * (m + 1)), prec);
-			QB_LOADF(m + 1, n - 2);
-			fast::mul(term, term, h, prec);
-			QB_LOADF(m + 2, n - 2);
-			fast::mul_small(t2, h, int64_t(4 * (m + 1) * (m + 2)), prec);
-			fast::add(term, term, t2, prec);
-			fast::add(val, val, term, prec);
-		}
-#undef QB_LOADF
 		// common_factor = 4 n eps + (4 n - 2) n
 		int64_t cn = int64_t(4 * n) * eps.num + int64_t(4 * n - 2) * int64_t(n) * int64_t(eps.den);
-		div_q(val, val, cn, eps.den, prec);
+		div_q(val, R[VAL], cn, eps.den, prec);
 	}
 	// h[m, n] = val + 8 h[m-3, n] + 4 h[m-2, n] - 2 h[m-1, n]; the three predecessors are handed in thread-local
 	// (p1 = h[m-1,n], p2 = h[m-2,n], p3 = h[m-3,n]); result thread-local                          (context.cpp:123-130)
