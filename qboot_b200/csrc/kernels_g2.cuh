@@ -43,6 +43,43 @@ namespace qb
 		for (int j = 0; j < L; ++j) v.m[j] = my[j * QB_DERIV_THREADS];
 	}
 
+	// 64-bit record transfers: records are 4 (L + 2) bytes apart in arrays whose base is 256-byte aligned, so for even L
+	// every record is 8-byte aligned and moves as (L + 2) / 2 double words -- half the load / store instructions of the
+	// word-wise copy() (k_scale was throttled by its memory-instruction queue: 34 STG + 34 LDG + 32 STS + 32 LDS per step).
+	template <int L>
+	__device__ __forceinline__ void load_rec(mpf<L>& d, const mpf<L>* src)
+	{
+		if constexpr (L % 2 == 0)
+		{
+			const uint2* sp = reinterpret_cast<const uint2*>(src);
+			uint2 v = sp[0];
+			d.sk = v.x;
+			d.exp = int32_t(v.y);
+#pragma unroll
+			for (int j = 0; j < L / 2; ++j)
+			{
+				v = sp[1 + j];
+				d.m[2 * j] = v.x;
+				d.m[2 * j + 1] = v.y;
+			}
+		}
+		else
+			copy(d, *src);
+	}
+	template <int L>
+	__device__ __forceinline__ void store_rec(mpf<L>* dst, const mpf<L>& s)
+	{
+		if constexpr (L % 2 == 0)
+		{
+			uint2* dp = reinterpret_cast<uint2*>(dst);
+			dp[0] = make_uint2(s.sk, uint32_t(s.exp));
+#pragma unroll
+			for (int j = 0; j < L / 2; ++j) dp[1 + j] = make_uint2(s.m[2 * j], s.m[2 * j + 1]);
+		}
+		else
+			copy(*dst, s);
+	}
+
 	// rho-derivative stage, part 1: every scaled coefficient array a_k[n], k = 0..lambda (reference: h *= 4^Delta,
 	// src/hor_recursion.cpp:43, then lambda times RealFunctionWithPower::derivate, real_function.hpp:236-240):
 	//   a_0[n] = b[n] * 4^Delta,   a_k[n] = a_{k-1}[n] * (q_{k-1} + n),   q_k = q_{k-1} - 1,  q_0 = Delta  (q_k from k_pow)
@@ -82,14 +119,15 @@ namespace qb
 			}
 			else
 				fast::mul(cur, b[size_t(tr.job0) * n1 + n], pt[0], prec);
-			copy(at[0], cur);
+			store_rec(&at[0], cur);
 			chain_store(my, csk, cexp, cur);
 		}
 		QB_ROLL
 		for (int k = 1; k < nk; ++k)
 		{
-			mpf<L> f, nxt;
-			fast::add_small(f, pt[nk + k], int64_t(n), prec);   // q_{k-1} + n
+			mpf<L> f, nxt, qk;
+			load_rec(qk, &pt[nk + k]);
+			fast::add_small(f, qk, int64_t(n), prec);   // q_{k-1} + n
 			if ((csk & 3u) == K_REG && (f.sk & 3u) == K_REG)
 				fast::mul_strided<L, QB_DERIV_THREADS>(nxt, csk, cexp, my, f, prec);
 			else
@@ -98,7 +136,7 @@ namespace qb
 				chain_load(cur, my, csk, cexp);
 				mul(nxt, cur, f, prec);
 			}
-			copy(at[size_t(k) * n1], nxt);
+			store_rec(&at[size_t(k) * n1], nxt);
 			chain_store(my, csk, cexp, nxt);
 		}
 	}
