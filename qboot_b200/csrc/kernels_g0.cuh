@@ -56,6 +56,41 @@ namespace qb
 		for (int k = 0; k < st; ++k) copy(out[i * st + k], pe[k]);
 	}
 
+	// 64-bit record transfers (see kernels_g2.cuh): for even L every record of a 256-byte aligned array is 8-byte aligned
+	template <int L>
+	__device__ __forceinline__ void load_rec64(mpf<L>& d, const mpf<L>* src)
+	{
+		if constexpr (L % 2 == 0)
+		{
+			const uint2* sp = reinterpret_cast<const uint2*>(src);
+			uint2 v = sp[0];
+			d.sk = v.x;
+			d.exp = int32_t(v.y);
+#pragma unroll
+			for (int j = 0; j < L / 2; ++j)
+			{
+				v = sp[1 + j];
+				d.m[2 * j] = v.x;
+				d.m[2 * j + 1] = v.y;
+			}
+		}
+		else
+			copy(d, *src);
+	}
+	template <int L>
+	__device__ __forceinline__ void store_rec64(mpf<L>* dst, const mpf<L>& s)
+	{
+		if constexpr (L % 2 == 0)
+		{
+			uint2* dp = reinterpret_cast<uint2*>(dst);
+			dp[0] = make_uint2(s.sk, uint32_t(s.exp));
+#pragma unroll
+			for (int j = 0; j < L / 2; ++j) dp[1 + j] = make_uint2(s.m[2 * j], s.m[2 * j + 1]);
+		}
+		else
+			copy(*dst, s);
+	}
+
 	// values of the K recurrence polynomials at every n: pv[(job * n_max + n - 1) * 8 + i] = p_i(n), by Horner with the
 	// integer n (include/qboot/algebra/polynomial.hpp:66-83).  They do not depend on the series, so they are taken off its
 	// sequential chain: one thread per (job, n).
@@ -80,15 +115,16 @@ namespace qb
 		QB_ROLL
 		for (int i = 0; i < K; ++i)
 		{
-			mpf<L> s;
-			copy(s, c[i * st + deg]);
+			mpf<L> s, cd;
+			load_rec64(s, &c[i * st + deg]);
 			QB_ROLL
 			for (int d = deg - 1; d >= 0; --d)
 			{
 				fast::mul_small(s, s, int64_t(n), cx.prec);
-				fast::add(s, s, c[i * st + d], cx.prec);
+				load_rec64(cd, &c[i * st + d]);
+				fast::add(s, s, cd, cx.prec);
 			}
-			copy(out[i], s);
+			store_rec64(&out[i], s);
 		}
 	}
 
