@@ -27,6 +27,32 @@ def hostemu():
     return ctypes.CDLL(out)
 
 
+def _build_host_lib(out, srcs, deps, extra=()):
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-I" + os.path.join(ROOT, "include"), "-o", out, *srcs, *extra])
+
+
+def _tree(*dirs):
+    out = []
+    for d in dirs:
+        for base, _, files in os.walk(os.path.join(ROOT, d)):
+            out += [os.path.join(base, f) for f in files if f.endswith((".cpp", ".hpp", ".h", ".cuh", ".inc"))]
+    return out
+
+
+@pytest.fixture(scope="session")
+def hostfacade():
+    """Host arithmetic + ConformalScale of the C++ façade behind test-only C entry points (tests/hostemu/*_capi.cpp)."""
+    import ctypes
+
+    out = os.path.join(ROOT, "tests", "_build", "libqb_hostops_test.so")
+    srcs = [os.path.join(ROOT, "tests", "hostemu", f) for f in ("hostops_capi.cpp", "facade_scale_capi.cpp")]
+    srcs += [os.path.join(ROOT, "qboot_b200", "host", f) for f in ("hostops.cpp", "facade_math.cpp")]
+    _build_host_lib(out, srcs, srcs + _tree("include", "qboot_b200/host", "qboot_b200/csrc"))
+    return ctypes.CDLL(out)
+
+
 @pytest.fixture(scope="session")
 def ref():
     """The unmodified reference (oracle/_ref); built on demand where /root/reference exists."""
