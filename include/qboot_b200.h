@@ -22,6 +22,7 @@
 #ifndef QBOOT_B200_H_
 #define QBOOT_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -101,6 +102,15 @@ uint64_t qb_stream(const qb_handle* h);
 int qb_fblock_batch(qb_handle* h, int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
                     const int32_t* sym, uint32_t* out);
 
+/* v^d = ((1 - z)(1 - zbar))^d as tables -- ::v_to_d (src/context.cpp:28-42): d = n_d records, out = n_d * dim_M records (HOST). */
+int qb_vtod_batch(qb_handle* h, int n_d, const uint32_t* d, uint32_t* out);
+/* Context::F_block(d, gBlock, sym) for tables supplied by the caller (include/qboot/context.hpp:123-128): term i multiplies
+ * table i (g + i * dim_M records, HOST) by v^d[i]; out as in qb_fblock_batch.  The resident tables are not touched. */
+int qb_fblock_tables(qb_handle* h, int m, const uint32_t* g, const uint32_t* d, const int32_t* sym, uint32_t* out);
+/* Page-locked host memory for the bulk transfers of this library (tables out, SDPB text out); NULL on failure. */
+void* qb_pinned_alloc(size_t bytes);
+void qb_pinned_free(void* p);
+
 /* Measurement support.  qb_set_timing(h, 1) brackets each kernel of qb_gblock_run with CUDA events on the handle's
  * stream (chunks then run back to back on that one stream); qb_kernel_times synchronises and returns the device times
  * in ms of the last run: [0] recurrence coefficients, [1] polynomial values + series recurrence, [2] powers +
@@ -118,6 +128,67 @@ int qb_imad_peak(qb_handle* h, int iters, double* macs_per_s);
  * path uses; the entry exists so that the device build of each can be pinned against MPFR.  Needs a context. */
 int qb_op_batch(qb_handle* h, int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c,
                 const int64_t* ia, const int64_t* ib, uint32_t* out);
+
+/* ---- Polynomial matrix program (PMP) on the device -------------------------------------------------------------------
+ * Replaces the host loops of BootstrapEquation::make_cont_mat / make_disc_mat (src/bootstrap_equation.cpp:380-461),
+ * PolynomialProgram::create_input (src/polynomial_program.cpp:152-232) and the number formatting of SDPBInput::write
+ * (src/sdpb_input.cpp:17-36, include/qboot/mp/real.hpp:987-1030).  The block tables of the last qb_gblock_run stay in
+ * HBM; F/H products, the sums over the terms of each crossing equation, the elimination of the normalisation and the
+ * conversion to decimal text all happen there, and only the text of the SDPB files crosses PCIe.
+ *
+ * A *constraint block* is one positivity constraint (sector, operator): sz x sz symmetric matrices at n_samples = D + 1
+ * sample points for each of the N = sum(eq_dim) functional components.  Its values are stored as
+ *   M[p][n],  p = rc * n_samples + k,  rc = r (r + 1) / 2 + c  (c <= r, the lower triangle),  n = 0 .. N - 1
+ * which is the row order of the reference's d_B (rows enumerate (r, c <= r, k), polynomial_program.cpp:205-221).        */
+typedef struct qb_pmp_term
+{
+	int32_t eq;   /* index of the equation the term belongs to */
+	int32_t rc;   /* matrix position: max(r,c) (max(r,c) + 1) / 2 + min(r,c) */
+	int32_t tab0; /* block table of sample k = tab[tab0 + k], an index into the tables of the last qb_gblock_run */
+	int32_t d;    /* index into `d` (the power of v: (Delta_2 + Delta_3) / 2 of the term's externals) */
+	int32_t coef; /* index into `coef`: term.coeff() / (r == c ? 1 : 2) already rounded as the reference rounds it; -1 = 1 */
+} qb_pmp_term;
+typedef struct qb_pmp_block
+{
+	int32_t n_samples, sz; /* D + 1 and the matrix size */
+	int32_t term0, n_terms; /* this block's terms, in the order the equations list them */
+} qb_pmp_block;
+/* Assemble all blocks of a program: for every block, position, sample and component
+ *   M = sum over the terms of that (equation, position), in order, of coef * [2 proj_sym(v^d g_table)]_component
+ * added onto +0 (bootstrap_equation.cpp:399-405,447-453).  eq_dim[e] must equal qb_block_dim(eq_sym[e]).
+ * d: n_d records, coef: n_coef records (HOST).  Drops the blocks of any earlier program on this handle. */
+int qb_pmp_assemble(qb_handle* h, int n_eq, const int32_t* eq_dim, const int32_t* eq_sym, int n_blocks,
+                    const qb_pmp_block* blocks, int n_terms, const qb_pmp_term* terms, int n_tab, const int32_t* tab,
+                    int n_d, const uint32_t* d, int n_coef, const uint32_t* coef);
+/* Add a block computed elsewhere (discrete sectors contracted with OPE vectors, user-supplied inequalities):
+ * mat = schur * N records in the M[p][n] layout, target = schur records or NULL for zero.  Returns its block index. */
+int qb_pmp_block_add(qb_handle* h, int n_samples, int sz, const uint32_t* mat, const uint32_t* target);
+/* Read a block back: schur * N records. */
+int qb_pmp_block_fetch(qb_handle* h, int block, uint32_t* out);
+/* PolynomialProgram::create_input for the blocks sel[0..n_sel): with the n_elim variables lead[e] eliminated through
+ *   y[lead_e] + sum_m eqn[e][free_m] y[free_m] = eqn_target[e]
+ * d_B[p][m] = -M[p][free_m] and d_c[p] = -target[p], then for e = 0 .. n_elim - 1 an fma with M[p][lead_e]
+ * (polynomial_program.cpp:205-221).  eqn: n_elim * N records, eqn_target: n_elim records (HOST). */
+int qb_pmp_pack(qb_handle* h, int n_sel, const int32_t* sel, int n_elim, const int32_t* lead, int n_free,
+                const int32_t* free_idx, const uint32_t* eqn, const uint32_t* eqn_target);
+/* d_B (schur * n_free records, row-major) and d_c (schur records) of the j-th selected block; either may be NULL. */
+int qb_pmp_packed_fetch(qb_handle* h, int j, uint32_t* B, uint32_t* c);
+/* SDPB text of every packed number, formatted on the device: `ndigits` significant digits, mpfr_get_str rounding, the
+ * reference's default-float layout, one number per line.  sizes[2 j] / sizes[2 j + 1] = bytes of the d_B / d_c text of
+ * selected block j; qb_pmp_text_fetch copies the concatenation (block 0 d_B, block 0 d_c, block 1 d_B, ...) to HOST.
+ * Returns 0, or the count of numbers whose exponent is outside the device formatter's range: read them with
+ * qb_pmp_text_declined (idx = position in the stream, recs = the records), format them on the host and hand the text
+ * back with qb_pmp_text_patch (text i at texts + i * stride, len[i] bytes incl. the newline), which completes the call. */
+int qb_pmp_text(qb_handle* h, int ndigits, int64_t* sizes);
+int qb_pmp_text_declined(qb_handle* h, int cap, int64_t* idx, uint32_t* recs);
+int qb_pmp_text_patch(qb_handle* h, int cnt, const int64_t* idx, const char* texts, int stride, const int32_t* len,
+                      int64_t* sizes);
+int qb_pmp_text_fetch(qb_handle* h, char* out);
+/* out[0] blocks in the arena, [1] N, [2] records in the arena, [3] selected blocks of the last pack */
+int qb_pmp_info(const qb_handle* h, int64_t* out4);
+/* Diagnostic: n numbers (HOST) formatted on the device into slots of `slot` >= ndigits + 16 bytes; len[i] = bytes used
+ * or -1 when declined. */
+int qb_dec_format(qb_handle* h, int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* len);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,13 @@ SYMBOLS = (
     "qb_last_cuda_error", "qb_context_init", "qb_context_get", "qb_table_dim", "qb_block_dim", "qb_gblock_batch",
     "qb_gblock_plan", "qb_gblock_run", "qb_gblock_fetch", "qb_sync", "qb_gblock_device_tables", "qb_launch_count",
     "qb_stream", "qb_fblock_batch", "qb_op_batch", "qb_set_timing", "qb_kernel_times", "qb_imad_peak",
+    "qb_vtod_batch", "qb_fblock_tables", "qb_pinned_alloc", "qb_pinned_free",
+    "qb_pmp_assemble", "qb_pmp_block_add", "qb_pmp_block_fetch", "qb_pmp_pack", "qb_pmp_packed_fetch", "qb_pmp_text",
+    "qb_pmp_text_declined", "qb_pmp_text_patch", "qb_pmp_text_fetch", "qb_pmp_info", "qb_dec_format",
 )
+# the C++ facade (namespace qboot, include/qboot/*.hpp) built next to the C-ABI library; Python reaches it through the
+# model-level C entry points of qboot_b200/host/models_capi.cpp
+FACADE_PATH = os.path.join(_HERE, "libqboot.so")
 
 
 class QbError(RuntimeError):
@@ -68,8 +74,61 @@ def load_library():
     lib.qb_set_timing.argtypes = [C.c_void_p, C.c_int]
     lib.qb_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.qb_imad_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    lib.qb_vtod_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.qb_fblock_tables.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    lib.qb_pinned_alloc.argtypes = [C.c_size_t]
+    lib.qb_pinned_alloc.restype = C.c_void_p
+    lib.qb_pinned_free.argtypes = [C.c_void_p]
+    lib.qb_pinned_free.restype = None
+    lib.qb_pmp_assemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.qb_pmp_block_add.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.qb_pmp_block_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.qb_pmp_pack.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.qb_pmp_packed_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.qb_pmp_text.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.qb_pmp_text_declined.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.qb_pmp_text_patch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.qb_pmp_text_fetch.argtypes = [C.c_void_p, C.c_void_p]
+    lib.qb_pmp_info.argtypes = [C.c_void_p, C.c_void_p]
+    lib.qb_dec_format.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     _lib = lib
     return lib
+
+
+_facade = None
+
+
+def load_facade(path: str | None = None):
+    """Load the C++ facade library (libqboot.so); it links against the CUDA engine, so the same no-CPU-path rule holds."""
+    global _facade
+    if path is None and _facade is not None:
+        return _facade
+    p = path or FACADE_PATH
+    if not os.path.exists(p):
+        raise QbError(f"{p} is missing: build it with `python -m qboot_b200.build`")
+    lib = C.CDLL(p)
+    lib.qbf_last_error.restype = C.c_char_p
+    lib.qbf_build_pmp.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p,
+                                  C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_void_p, C.c_void_p]
+    if path is None:
+        _facade = lib
+    return lib
+
+
+def build_pmp(prec, n_max, lam, dim="3", model=0, mode=0, finite=True, ds="0.5181489", de="1.412625", de1="3.83", numax=8,
+              maxspin=24, threads=1, outdir=None, lib=None):
+    """convert -> create_input -> write of one of the reference's model problems through the C++ facade
+    (qboot::Context / BootstrapEquation / PolynomialProgram / SDPBInput on the GPU engine); see host/models_capi.cpp.
+    Returns the phase times and sizes like oracle/ref.py::build_pmp does for the reference."""
+    lib = lib or load_facade()
+    times = (C.c_double * 3)()
+    counts = (C.c_int64 * 3)()
+    rc = lib.qbf_build_pmp(prec, n_max, lam, str(dim).encode(), model, mode, int(finite), ds.encode(), de.encode(), de1.encode(),
+                           numax, maxspin, threads, (outdir or "").encode(), times, counts)
+    if rc != 0:
+        raise QbError("qbf_build_pmp: " + lib.qbf_last_error().decode())
+    return dict(convert=times[0], create_input=times[1], write=times[2], constraints=counts[0], N=counts[1], free=counts[2])
 
 
 def nlimbs(prec: int) -> int:

@@ -19,10 +19,15 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 BUILD = os.path.join(ROOT, "build", "qb")
 LIB = os.path.join(HERE, "libqboot_b200.so")
+# the C++ facade (include/qboot/*.hpp + qboot_b200/host/*.cpp): plain host C++17, reaches CUDA only through the C ABI above
+FACADE = os.path.join(HERE, "libqboot.so")
+HOST = os.path.join(HERE, "host")
+HOST_SRCS = ("hostops.cpp", "facade_math.cpp", "facade_context.cpp", "facade_program.cpp", "models_capi.cpp")
+CXX = os.environ.get("CXX", "g++")
 
 # limb counts compiled in: 512, 600, 800, 1000/1024, 1200, 1536 bits (override: QB_LIMBS=19,32)
 LIMBS = tuple(int(x) for x in os.environ.get("QB_LIMBS", "16,19,25,32,38,48").split(","))
-KGROUPS = (0, 1, 2, 3, 4)
+KGROUPS = (0, 1, 2, 3, 4, 5)
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -62,7 +67,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
     for L in LIMBS:
         for g in KGROUPS:
-            add(f"kernels_L{L}_g{g}", "kernel_inst.cu", [f"-DQB_L={L}", f"-DQB_KGROUP={g}"])
+            add(f"kernels_L{L}_g{g}", "kernel_inst.cu", [f"-DQB_L={L}", f"-DQB_KGROUP={g}", f"-DQB_L_FIRST={LIMBS[0]}"])
     for L in LIMBS:
         add(f"engine_L{L}", "engine_inst.cu", [f"-DQB_L={L}"])
     add("capi", "capi.cu", ["-DQB_L_LIST=" + " ".join(f"X({L})" for L in LIMBS)])
@@ -85,7 +90,36 @@ def build(force: bool = False, verbose: bool = True) -> str:
         _run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "shared"], os.path.join(BUILD, "link.log"))
         if verbose:
             print(f"built {LIB} ({len(todo)} objects compiled)")
+    build_facade(force=force, verbose=verbose)
     return LIB
+
+
+def build_facade(force: bool = False, verbose: bool = True, engine_lib: str = LIB, out: str = FACADE) -> str:
+    """g++ build of the C++ facade into qboot_b200/libqboot.so, linked against the C-ABI library next to it."""
+    os.makedirs(BUILD, exist_ok=True)
+    inc = os.path.join(ROOT, "include")
+    deps = [os.path.join(HOST, f) for f in os.listdir(HOST)]
+    for base, _, files in os.walk(inc):
+        deps += [os.path.join(base, f) for f in files]
+    deps += [os.path.join(CSRC, f) for f in ("mpf.cuh", "fastops.cuh", "mpf_math.cuh", "hostmath.hpp")]
+    tag = os.path.basename(out)
+    objs, todo = [], []
+    for src in HOST_SRCS:
+        obj = os.path.join(BUILD, f"{tag}.{src}.o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
+            todo.append(([CXX, "-std=c++17", "-O2", "-fPIC", "-pthread", "-w", "-I" + inc, "-c", os.path.join(HOST, src), "-o", obj],
+                         os.path.join(BUILD, f"{tag}.{src}.log")))
+    if todo or not os.path.exists(out) or os.path.getmtime(engine_lib) > os.path.getmtime(out):
+        with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+            for f in [ex.submit(_run, cmd, log) for cmd, log in todo]:
+                f.result()
+        libdir, libname = os.path.split(engine_lib)
+        _run([CXX, "-shared", "-o", out, *objs, "-L" + libdir, "-l:" + libname, "-Wl,-rpath,$ORIGIN", "-pthread"],
+             os.path.join(BUILD, f"{tag}.link.log"))
+        if verbose:
+            print(f"built {out} ({len(todo)} objects compiled)")
+    return out
 
 
 if __name__ == "__main__":

@@ -58,6 +58,21 @@ struct qb_handle
 	qb::EngineBase* e;
 };
 
+// nothing may throw across the C ABI: host-side planning allocates (std::vector, std::thread)
+#define QB_GUARDED(expr)               \
+	try                                \
+	{                                  \
+		return (expr);                 \
+	}                                  \
+	catch (const std::bad_alloc&)      \
+	{                                  \
+		return QB_ERR_NO_MEMORY;       \
+	}                                  \
+	catch (...)                        \
+	{                                  \
+		return QB_ERR_BAD_ARG;         \
+	}
+
 static qb::EngineFactory factory_for(int L)
 {
 	switch (L)
@@ -124,7 +139,7 @@ extern "C"
 	const char* qb_last_cuda_error(const qb_handle* h) { return h ? h->e->cuda_error.c_str() : ""; }
 	int qb_context_init(qb_handle* h, uint32_t n_max, uint32_t lambda, int64_t en, uint32_t ed)
 	{
-		return h ? h->e->context_init(n_max, lambda, en, ed) : QB_ERR_BAD_ARG;
+		QB_GUARDED(h ? h->e->context_init(n_max, lambda, en, ed) : QB_ERR_BAD_ARG)
 	}
 	int qb_context_get(const qb_handle* h, uint32_t* rho, uint32_t* mat)
 	{
@@ -138,9 +153,9 @@ extern "C"
 	int qb_gblock_plan(qb_handle* h, int n, const uint32_t* spin, const uint32_t* delta, const uint32_t* S,
 	                   const uint32_t* P)
 	{
-		return h ? h->e->gblock_plan(n, spin, delta, S, P) : QB_ERR_BAD_ARG;
+		QB_GUARDED(h ? h->e->gblock_plan(n, spin, delta, S, P) : QB_ERR_BAD_ARG)
 	}
-	int qb_gblock_run(qb_handle* h) { return h ? h->e->gblock_run() : QB_ERR_BAD_ARG; }
+	int qb_gblock_run(qb_handle* h) { QB_GUARDED(h ? h->e->gblock_run() : QB_ERR_BAD_ARG) }
 	int qb_gblock_fetch(qb_handle* h, uint32_t* out) { return (h && out) ? h->e->gblock_fetch(out) : QB_ERR_BAD_ARG; }
 	int qb_sync(qb_handle* h)
 	{
@@ -181,13 +196,20 @@ extern "C"
 	{
 		if (!h) return QB_ERR_BAD_ARG;
 		if (n > 0 && !out) return QB_ERR_BAD_ARG;
-		int rc = h->e->gblock_plan(n, spin, delta, S, P);
+		int rc = qb_gblock_plan(h, n, spin, delta, S, P);
 		if (rc) return rc;
 		// every chunk is copied out as soon as it is finished, underneath the later chunks
 		h->e->fetch_dst = out;
-		rc = h->e->gblock_run();
+		rc = qb_gblock_run(h);
 		h->e->fetch_dst = nullptr;
-		if (rc) return rc;
+		if (rc)
+		{
+			// drain whatever was queued before the failure: copies into `out` must not outlive the call
+			cudaSetDevice(h->e->device);
+			cudaDeviceSynchronize();
+			cudaGetLastError();
+			return rc;
+		}
 		return qb_sync(h);
 	}
 	int qb_op_batch(qb_handle* h, int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c,
@@ -198,6 +220,63 @@ extern "C"
 	int qb_fblock_batch(qb_handle* h, int m, const int32_t* table_idx, int n_d, const uint32_t* d, const int32_t* d_idx,
 	                    const int32_t* sym, uint32_t* out)
 	{
-		return h ? h->e->fblock_batch(m, table_idx, n_d, d, d_idx, sym, out) : QB_ERR_BAD_ARG;
+		QB_GUARDED(h ? h->e->fblock_batch(m, table_idx, n_d, d, d_idx, sym, out) : QB_ERR_BAD_ARG)
+	}
+	int qb_vtod_batch(qb_handle* h, int n_d, const uint32_t* d, uint32_t* out) { QB_GUARDED(h ? h->e->vtod_batch(n_d, d, out) : QB_ERR_BAD_ARG) }
+	int qb_fblock_tables(qb_handle* h, int m, const uint32_t* g, const uint32_t* d, const int32_t* sym, uint32_t* out)
+	{
+		QB_GUARDED(h ? h->e->fblock_tables(m, g, d, sym, out) : QB_ERR_BAD_ARG)
+	}
+	void* qb_pinned_alloc(size_t bytes)
+	{
+		void* p = nullptr;
+		if (bytes == 0) return nullptr;
+		if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
+		{
+			cudaGetLastError();
+			return nullptr;
+		}
+		return p;
+	}
+	void qb_pinned_free(void* p)
+	{
+		if (p) cudaFreeHost(p);
+	}
+	// ---- PMP stage ----
+	static_assert(sizeof(qb_pmp_term) == 20, "qb_pmp_term layout: five int32, as qb::PmpTerm (pmp.cuh)");
+	static_assert(sizeof(qb_pmp_block) == 16, "qb_pmp_block layout");
+	int qb_pmp_assemble(qb_handle* h, int n_eq, const int32_t* eq_dim, const int32_t* eq_sym, int n_blocks,
+	                    const qb_pmp_block* blocks, int n_terms, const qb_pmp_term* terms, int n_tab, const int32_t* tab,
+	                    int n_d, const uint32_t* d, int n_coef, const uint32_t* coef)
+	{
+		QB_GUARDED(h ? h->e->pmp_assemble(n_eq, eq_dim, eq_sym, n_blocks, reinterpret_cast<const int32_t*>(blocks), n_terms,
+		                                  reinterpret_cast<const int32_t*>(terms), n_tab, tab, n_d, d, n_coef, coef)
+		             : QB_ERR_BAD_ARG)
+	}
+	int qb_pmp_block_add(qb_handle* h, int n_samples, int sz, const uint32_t* mat, const uint32_t* target)
+	{
+		QB_GUARDED(h ? h->e->pmp_block_add(n_samples, sz, mat, target) : QB_ERR_BAD_ARG)
+	}
+	int qb_pmp_block_fetch(qb_handle* h, int block, uint32_t* out) { QB_GUARDED(h ? h->e->pmp_block_fetch(block, out) : QB_ERR_BAD_ARG) }
+	int qb_pmp_pack(qb_handle* h, int n_sel, const int32_t* sel, int n_elim, const int32_t* lead, int n_free,
+	                const int32_t* free_idx, const uint32_t* eqn, const uint32_t* eqn_target)
+	{
+		QB_GUARDED(h ? h->e->pmp_pack(n_sel, sel, n_elim, lead, n_free, free_idx, eqn, eqn_target) : QB_ERR_BAD_ARG)
+	}
+	int qb_pmp_packed_fetch(qb_handle* h, int j, uint32_t* B, uint32_t* c) { QB_GUARDED(h ? h->e->pmp_packed_fetch(j, B, c) : QB_ERR_BAD_ARG) }
+	int qb_pmp_text(qb_handle* h, int ndigits, int64_t* sizes) { QB_GUARDED(h ? h->e->pmp_text(ndigits, sizes) : QB_ERR_BAD_ARG) }
+	int qb_pmp_text_declined(qb_handle* h, int cap, int64_t* idx, uint32_t* recs)
+	{
+		QB_GUARDED((h && idx && recs && cap >= 0) ? h->e->pmp_text_declined(cap, idx, recs) : QB_ERR_BAD_ARG)
+	}
+	int qb_pmp_text_patch(qb_handle* h, int cnt, const int64_t* idx, const char* texts, int stride, const int32_t* len, int64_t* sizes)
+	{
+		QB_GUARDED(h ? h->e->pmp_text_patch(cnt, idx, texts, stride, len, sizes) : QB_ERR_BAD_ARG)
+	}
+	int qb_pmp_text_fetch(qb_handle* h, char* out) { QB_GUARDED(h ? h->e->pmp_text_fetch(out) : QB_ERR_BAD_ARG) }
+	int qb_pmp_info(const qb_handle* h, int64_t* out4) { return (h && out4) ? h->e->pmp_info(out4) : QB_ERR_BAD_ARG; }
+	int qb_dec_format(qb_handle* h, int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* len)
+	{
+		QB_GUARDED(h ? h->e->dec_format(ndigits, n, x, slots, slot, len) : QB_ERR_BAD_ARG)
 	}
 }

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -42,6 +43,23 @@ namespace qb
 		uint32_t* fetch_dst = nullptr;
 		virtual int op_batch(int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c, const int64_t* ia,
 		                     const int64_t* ib, uint32_t* out) = 0;
+		virtual int vtod_batch(int n_d, const uint32_t* d, uint32_t* out) = 0;
+		virtual int fblock_tables(int m, const uint32_t* g, const uint32_t* d, const int32_t* sym, uint32_t* out) = 0;
+		// PMP stage (see include/qboot_b200.h, qb_pmp_*)
+		virtual int pmp_assemble(int n_eq, const int32_t* eq_dim, const int32_t* eq_sym, int n_blocks, const int32_t* blocks4,
+		                         int n_terms, const int32_t* terms5, int n_tab, const int32_t* tab, int n_d, const uint32_t* d,
+		                         int n_coef, const uint32_t* coef) = 0;
+		virtual int pmp_block_add(int n_samples, int sz, const uint32_t* mat, const uint32_t* target) = 0;
+		virtual int pmp_block_fetch(int block, uint32_t* out) = 0;
+		virtual int pmp_pack(int n_sel, const int32_t* sel, int n_elim, const int32_t* lead, int n_free, const int32_t* free_idx,
+		                     const uint32_t* eqn, const uint32_t* eqn_target) = 0;
+		virtual int pmp_packed_fetch(int j, uint32_t* B, uint32_t* c) = 0;
+		virtual int pmp_text(int ndigits, int64_t* sizes) = 0;
+		virtual int pmp_text_declined(int cap, int64_t* idx, uint32_t* recs) = 0;
+		virtual int pmp_text_patch(int cnt, const int64_t* idx, const char* texts, int stride, const int32_t* len, int64_t* sizes) = 0;
+		virtual int pmp_text_fetch(char* out) = 0;
+		virtual int pmp_info(int64_t* out4) const = 0;
+		virtual int dec_format(int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* len) = 0;
 	};
 	typedef EngineBase* (*EngineFactory)(int device, int prec);
 }  // namespace qb
@@ -75,6 +93,28 @@ namespace qb
 			cap = want;
 			return 0;
 		}
+		// like ensure, but the first `keep` bytes survive a reallocation
+		int grow(size_t bytes, size_t keep)
+		{
+			if (bytes <= cap) return 0;
+			void* q = nullptr;
+			size_t want = bytes + bytes / 4 + 256;
+			if (cudaMalloc(&q, want) != cudaSuccess)
+			{
+				cudaGetLastError();
+				return -1;
+			}
+			if (p && keep && cudaMemcpy(q, p, keep, cudaMemcpyDeviceToDevice) != cudaSuccess)
+			{
+				cudaGetLastError();
+				cudaFree(q);
+				return -1;
+			}
+			if (p) cudaFree(p);
+			p = q;
+			cap = want;
+			return 0;
+		}
 		void release()
 		{
 			if (p) cudaFree(p);
@@ -98,9 +138,10 @@ namespace qb
 		Rational eps{0, 1};
 		ContextConsts<L> consts;
 		std::map<uint32_t, T> b0_cache;
-		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_qc, d_pv, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms;
+		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_qc, d_pv, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms, d_fb_g;
 		DevCtx cx{};
 		int n_tables = 0, n_jobs = 0;
+		bool tables_valid = false;  // a gblock_run has completed for the current plan
 		// layout of d_in: [delta | S | P] (tables) then spin; d_jobs: [delta | S | P | b0] (jobs) then spin
 		T *t_delta = nullptr, *t_S = nullptr, *t_P = nullptr;
 		uint32_t* t_spin = nullptr;
@@ -128,8 +169,13 @@ namespace qb
 		{
 			cudaSetDevice(device);
 			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_qc, &d_pv, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
-			                  &d_fb_terms})
+			                  &d_fb_terms, &d_fb_g})
 				b->release();
+			pmp_release();
+			for (cudaEvent_t e_ : ev) cudaEventDestroy(e_);
+			for (cudaEvent_t e_ : dep_ev) cudaEventDestroy(e_);
+			for (cudaEvent_t e_ : {fork_ev, copy_done_ev, fin_done_ev, lo_done_ev})
+				if (e_) cudaEventDestroy(e_);
 			for (cudaStream_t s : hi_streams) cudaStreamDestroy(s);
 			for (cudaStream_t s_ : {lo_stream, mid_stream, fin_stream, copy_stream})
 				if (s_) cudaStreamDestroy(s_);
@@ -161,7 +207,22 @@ namespace qb
 		int context_init(uint32_t nmax, uint32_t lam, int64_t en, uint32_t ed) override
 		{
 			if (ed == 0 || lam > 200 || nmax == 0) return -4;
+			{
+				// the kernels hand small integers derived from epsilon to div_q / add_q / set_q (32-bit divisors): the transverse
+				// recursion divides by 4 n eps + (4 n - 2) n (block.cuh), the Casimir uses 2 den; refuse what does not fit
+				const int64_t an = en < 0 ? -en : en, nr = std::max<int64_t>(1, int64_t(lam) / 2);
+				if (an >= (int64_t(1) << 40) || 2 * int64_t(ed) >= (int64_t(1) << 32)) return -6;
+				const int64_t cn = 4 * nr * an + (4 * nr - 2) * nr * int64_t(ed);
+				if (cn >= (int64_t(1) << 32)) return -6;
+			}
 			QB_CU(cudaSetDevice(device));
+			// a new context invalidates the plan, the tables and the PMP blocks of the previous one
+			n_tables = n_jobs = 0;
+			tables_valid = false;
+			pm_blocks.clear();
+			pm_sel.clear();
+			pm_N = 0;
+			has_ctx = false;
 			n_max = nmax;
 			lambda = lam;
 			eps = Rational{en, ed};
@@ -284,6 +345,11 @@ namespace qb
 			add_si(onep, small, 1, prec);
 			neg(small);
 			add_si(onem, small, 1, prec);
+			for (int t = 0; t < n; ++t)
+			{
+				if ((hd[t].sk & 2u) || (hS[t].sk & 2u) || (hP[t].sk & 2u)) return -4;  // inf / nan
+				if (spin[t] > 400) return -6;
+			}
 			// the divergence test is the only per-table arithmetic of the planner: fan it out over host threads
 			std::vector<uint8_t> diverges(static_cast<size_t>(n), 0);
 			{
@@ -325,7 +391,9 @@ namespace qb
 					tr[size_t(t)].job1 = -1;
 				}
 			}
-			n_tables = n;
+			// from here on the previous plan is gone; the new one counts only once everything below has succeeded
+			n_tables = 0;
+			tables_valid = false;
 			n_jobs = int(jd.size());
 			job_of_table.assign(size_t(n) + 1, n_jobs);
 			for (int t = 0; t < n; ++t) job_of_table[size_t(t)] = tr[size_t(t)].job0;
@@ -381,6 +449,7 @@ namespace qb
 			QB_CU(cudaMemcpyAsync(j_spin, jsp.data(), 4 * nj, cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaMemcpyAsync(d_tref.p, tr.data(), sizeof(TableRef) * nt, cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaStreamSynchronize(stream));  // host vectors go out of scope
+			n_tables = n;
 			return 0;
 		}
 
@@ -490,6 +559,7 @@ namespace qb
 				for (int c = 0; c < n_chunks; ++c)
 					if (int rc = run_serial(c, stream, timing ? ev.data() + 5 * c : nullptr)) return rc;
 				QB_CU(cudaGetLastError());
+				tables_valid = true;
 				return 0;
 			}
 			if (!lo_stream)
@@ -565,6 +635,7 @@ namespace qb
 				QB_CU(cudaStreamWaitEvent(stream, copy_done_ev, 0));
 			}
 			QB_CU(cudaGetLastError());
+			tables_valid = true;
 			return 0;
 		}
 		// after a synchronise: read the per-kernel times of the last run
@@ -619,6 +690,7 @@ namespace qb
 		{
 			if (!has_ctx) return -3;
 			if (n_tables == 0) return 0;
+			if (!tables_valid) return -4;
 			QB_CU(cudaSetDevice(device));
 			size_t bytes = sizeof(T) * size_t(cf_dim(int(lambda))) * size_t(n_tables);
 			QB_CU(cudaMemcpyAsync(out, d_g.p, bytes, cudaMemcpyDeviceToHost, stream));
@@ -633,7 +705,7 @@ namespace qb
 			if (!has_ctx) return -3;
 			if (m < 0 || n_d < 0) return -4;
 			if (m == 0) return 0;
-			if (!table_idx || !d || !d_idx || !sym || !out || n_d == 0) return -4;
+			if (!table_idx || !d || !d_idx || !sym || !out || n_d == 0 || !tables_valid) return -4;
 			QB_CU(cudaSetDevice(device));
 			const int lam = int(lambda), dimM = cf_dim(lam);
 			const int dim_max = cf_dim_sym(lam, 0) > cf_dim_sym(lam, 1) ? cf_dim_sym(lam, 0) : cf_dim_sym(lam, 1);
@@ -667,6 +739,56 @@ namespace qb
 			QB_CU(cudaStreamSynchronize(stream));
 			return 0;
 		}
+		// v^d tables of n_d values (HOST in, HOST out: n_d * dim_M records)                     (src/context.cpp:28-42)
+		int vtod_batch(int n_d, const uint32_t* d, uint32_t* out) override
+		{
+			if (!has_ctx) return -3;
+			if (n_d <= 0) return n_d == 0 ? 0 : -4;
+			if (!d || !out) return -4;
+			QB_CU(cudaSetDevice(device));
+			const size_t dimM = size_t(cf_dim(int(lambda)));
+			if (d_fb_in.ensure(sizeof(T) * size_t(n_d)) || d_fb_v.ensure(sizeof(T) * size_t(n_d) * dimM)) return -7;
+			QB_CU(cudaMemcpyAsync(d_fb_in.p, d, sizeof(T) * size_t(n_d), cudaMemcpyHostToDevice, stream));
+			launch_vtod<L>(cx, n_d, d_fb_in.as<T>(), d_fb_v.as<T>(), stream);
+			++launches;
+			QB_CU(cudaGetLastError());
+			QB_CU(cudaMemcpyAsync(out, d_fb_v.p, sizeof(T) * size_t(n_d) * dimM, cudaMemcpyDeviceToHost, stream));
+			QB_CU(cudaStreamSynchronize(stream));
+			return 0;
+		}
+		// F/H blocks of m (table, d, sym) triples with the TABLES GIVEN BY THE CALLER (HOST, m * dim_M records): term i uses
+		// table i and d[i].  Leaves the resident tables of the last gblock_run untouched.
+		int fblock_tables(int m, const uint32_t* g, const uint32_t* d, const int32_t* sym, uint32_t* out) override
+		{
+			if (!has_ctx) return -3;
+			if (m <= 0) return m == 0 ? 0 : -4;
+			if (!g || !d || !sym || !out) return -4;
+			QB_CU(cudaSetDevice(device));
+			const int lam = int(lambda), dimM = cf_dim(lam);
+			const int dim_max = std::max(cf_dim_sym(lam, 0), cf_dim_sym(lam, 1));
+			std::vector<TermRef> terms(static_cast<size_t>(m));
+			int64_t ofs = 0;
+			for (int i = 0; i < m; ++i)
+			{
+				if (sym[i] != 0 && sym[i] != 1) return -4;
+				terms[size_t(i)] = TermRef{i, i, sym[i], int32_t(ofs)};
+				ofs += cf_dim_sym(lam, sym[i]);
+				if (ofs > 0x7fffffff) return -4;
+			}
+			if (d_fb_in.ensure(sizeof(T) * size_t(m)) || d_fb_v.ensure(sizeof(T) * size_t(m) * size_t(dimM)) || d_fb_g.ensure(sizeof(T) * size_t(m) * size_t(dimM)) ||
+			    d_fb_out.ensure(sizeof(T) * size_t(ofs)) || d_fb_terms.ensure(sizeof(TermRef) * size_t(m)))
+				return -7;
+			QB_CU(cudaMemcpyAsync(d_fb_in.p, d, sizeof(T) * size_t(m), cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(d_fb_g.p, g, sizeof(T) * size_t(m) * size_t(dimM), cudaMemcpyHostToDevice, stream));
+			QB_CU(cudaMemcpyAsync(d_fb_terms.p, terms.data(), sizeof(TermRef) * size_t(m), cudaMemcpyHostToDevice, stream));
+			launch_vtod<L>(cx, m, d_fb_in.as<T>(), d_fb_v.as<T>(), stream);
+			launch_fblock<L>(cx, m, dim_max, d_fb_terms.as<TermRef>(), d_fb_g.as<T>(), d_fb_v.as<T>(), d_fb_out.as<T>(), stream);
+			launches += 2;
+			QB_CU(cudaGetLastError());
+			QB_CU(cudaMemcpyAsync(out, d_fb_out.p, sizeof(T) * size_t(ofs), cudaMemcpyDeviceToHost, stream));
+			QB_CU(cudaStreamSynchronize(stream));
+			return 0;
+		}
 		int op_batch(int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c, const int64_t* ia,
 		             const int64_t* ib, uint32_t* out) override
 		{
@@ -694,15 +816,23 @@ namespace qb
 			QB_CU(cudaStreamSynchronize(stream));
 			return 0;
 		}
+#include "engine_pmp.inc"
 #undef QB_CU
 	};
 
 	template <int L>
 	EngineBase* make_engine(int device, int prec)
 	{
-		auto* e = new Engine<L>(device, prec);
+		auto* e = new (std::nothrow) Engine<L>(device, prec);
+		if (!e) return nullptr;
+		if (cudaSetDevice(device) != cudaSuccess)
+		{
+			cudaGetLastError();
+			delete e;
+			return nullptr;
+		}
 		if (const char* ss = std::getenv("QB_STACK_BYTES")) cudaDeviceSetLimit(cudaLimitStackSize, size_t(std::atol(ss)));
-		if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+		if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
 		{
 			cudaGetLastError();
 			delete e;

@@ -1,7 +1,8 @@
 // qboot_b200 -- kernel translation unit: nvcc -DQB_L=<limbs> -DQB_KGROUP=<0..4> kernel_inst.cu
 //   group 0: k_rec_coeffs, k_polyvals, k_ops    1: k_series    2: k_scale, k_horner    3: k_rho_to_z, k_offdiag_val, k_offdiag_close    4: k_vtod, k_fblock, k_pow
+//   group 5: k_pmp_accum, k_pmp_pack, k_dec_format, k_dec_gather (the last one is not templated: compiled once, -DQB_L_FIRST=<smallest L>)
 #if !defined(QB_L) || !defined(QB_KGROUP)
-#error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..4>"
+#error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..5>"
 #endif
 #include <cstdlib>
 #if QB_KGROUP == 0
@@ -12,8 +13,10 @@
 #include "kernels_g2.cuh"
 #elif QB_KGROUP == 3
 #include "kernels_g3.cuh"
-#else
+#elif QB_KGROUP == 4
 #include "kernels_g4.cuh"
+#else
+#include "kernels_g5.cuh"
 #endif
 
 namespace qb
@@ -103,6 +106,40 @@ namespace qb
 		int64_t total = int64_t(n_terms) * dim_max;
 		k_fblock<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_terms, dim_max, terms, g, v, out);
 	}
+#elif QB_KGROUP == 5
+	template <>
+	void launch_pmp_accum<QB_L>(const DevCtx& cx, int n_blocks, const PmpBlock* blocks, const PmpTerm* terms, const int32_t* tab,
+	                            int n_eq, const int32_t* eq_ofs, const int32_t* eq_sym, const mpf<QB_L>* g, const mpf<QB_L>* v,
+	                            const mpf<QB_L>* coef, mpf<QB_L>* Marena, int64_t total, cudaStream_t st)
+	{
+		const int threads = 128;
+		k_pmp_accum<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_blocks, blocks, terms, tab, n_eq, eq_ofs,
+		                                                                                 eq_sym, g, v, coef, Marena, total);
+	}
+	template <>
+	void launch_pmp_pack<QB_L>(const DevCtx& cx, int n_blocks, const PmpBlock* blocks, int N, int n_free, const int32_t* free_idx,
+	                           int n_elim, const int32_t* lead, const mpf<QB_L>* eqn, const mpf<QB_L>* eqn_target,
+	                           const mpf<QB_L>* Marena, const mpf<QB_L>* targets, mpf<QB_L>* Barena, mpf<QB_L>* Carena, int64_t total,
+	                           cudaStream_t st)
+	{
+		const int threads = 128;
+		k_pmp_pack<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_blocks, blocks, N, n_free, free_idx, n_elim,
+		                                                                                lead, eqn, eqn_target, Marena, targets, Barena,
+		                                                                                Carena, total);
+	}
+	template <>
+	void launch_dec_format<QB_L>(const DecTables& tb, int64_t n, const mpf<QB_L>* x, char* slots, int slot, int32_t* len, cudaStream_t st)
+	{
+		const int threads = 64;
+		k_dec_format<QB_L><<<unsigned((n + threads - 1) / threads), threads, 0, st>>>(tb, n, x, slots, slot, len);
+	}
+#if QB_L == QB_L_FIRST
+	void launch_dec_gather(int64_t n, const char* slots, int slot, const int32_t* len, const int64_t* ofs, char* text, cudaStream_t st)
+	{
+		const int threads = 256;
+		k_dec_gather<<<unsigned((n * 32 + threads - 1) / threads), threads, 0, st>>>(n, slots, slot, len, ofs, text);
+	}
+#endif
 #else
 #error "QB_KGROUP out of range"
 #endif

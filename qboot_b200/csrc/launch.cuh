@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "hor.cuh"
+#include "pmp.cuh"
 
 namespace qb
 {
@@ -63,6 +64,18 @@ namespace qb
 	template <int L>
 	void launch_ops(const DevCtx& cx, int op, int n, const mpf<L>* a, const mpf<L>* b, const mpf<L>* c, const int64_t* ia,
 	                const int64_t* ib, mpf<L>* out, cudaStream_t st);
+	// PMP stage (kernels_g5.cuh)
+	template <int L>
+	void launch_pmp_accum(const DevCtx& cx, int n_blocks, const PmpBlock* blocks, const PmpTerm* terms, const int32_t* tab, int n_eq,
+	                      const int32_t* eq_ofs, const int32_t* eq_sym, const mpf<L>* g, const mpf<L>* v, const mpf<L>* coef,
+	                      mpf<L>* Marena, int64_t total, cudaStream_t st);
+	template <int L>
+	void launch_pmp_pack(const DevCtx& cx, int n_blocks, const PmpBlock* blocks, int N, int n_free, const int32_t* free_idx,
+	                     int n_elim, const int32_t* lead, const mpf<L>* eqn, const mpf<L>* eqn_target, const mpf<L>* Marena,
+	                     const mpf<L>* targets, mpf<L>* Barena, mpf<L>* Carena, int64_t total, cudaStream_t st);
+	template <int L>
+	void launch_dec_format(const DecTables& tb, int64_t n, const mpf<L>* x, char* slots, int slot, int32_t* len, cudaStream_t st);
+	void launch_dec_gather(int64_t n, const char* slots, int slot, const int32_t* len, const int64_t* ofs, char* text, cudaStream_t st);
 	// integer multiply-add probe (capi.cu)
 	void launch_imad_peak(uint64_t* out, int iters, uint32_t seed, int blocks, int threads, cudaStream_t st);
 }  // namespace qb

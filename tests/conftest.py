@@ -54,6 +54,24 @@ def hostfacade():
 
 
 @pytest.fixture(scope="session")
+def facade_emu(ref):
+    """The C++ facade linked against a host stand-in of the C ABI (tests/hostemu/emu_capi.cpp: tables from the oracle,
+    PMP stages from the engine's own host+device source).  Lets the CPU suite run convert -> create_input -> write."""
+    import qboot_b200 as qb
+
+    bdir = os.path.join(ROOT, "tests", "_build")
+    emu = os.path.join(bdir, "libqb_emu.so")
+    deps = _tree("include", "qboot_b200/host", "qboot_b200/csrc", "tests/hostemu")
+    _build_host_lib(emu, [os.path.join(ROOT, "tests", "hostemu", "emu_capi.cpp"), os.path.join(ROOT, "qboot_b200", "host", "hostops.cpp")],
+                    deps, ["-ldl"])
+    fac = os.path.join(bdir, "libqboot_facade_emu.so")
+    srcs = [os.path.join(ROOT, "qboot_b200", "host", f) for f in ("facade_math.cpp", "facade_context.cpp", "facade_program.cpp", "models_capi.cpp")]
+    _build_host_lib(fac, srcs, deps + [emu], ["-L" + bdir, "-lqb_emu", "-Wl,-rpath,$ORIGIN", "-pthread"])
+    os.environ["QB_EMU_REF"] = os.path.join(ROOT, "oracle", "_ref", "libqboot_ref.so")
+    return qb.load_facade(fac)
+
+
+@pytest.fixture(scope="session")
 def ref():
     """The unmodified reference (oracle/_ref); built on demand where /root/reference exists."""
     from oracle import ref as r
