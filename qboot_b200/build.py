@@ -23,7 +23,9 @@ LIB = os.path.join(HERE, "libqboot_b200.so")
 FACADE = os.path.join(HERE, "libqboot.so")
 HOST = os.path.join(HERE, "host")
 HOST_SRCS = ("hostops.cpp", "facade_math.cpp", "facade_context.cpp", "facade_program.cpp", "models_capi.cpp")
-CXX = os.environ.get("CXX", "g++")
+# the system g++ on purpose: $CXX in this image names a toolchain that links its own libstdc++ statically, and two
+# libstdc++ copies in one process (this library + the nvcc-built one) crash in iostream code
+CXX = os.environ.get("QB_CXX", "/usr/bin/g++")
 
 # limb counts compiled in: 512, 600, 800, 1000/1024, 1200, 1536 bits (override: QB_LIMBS=19,32)
 LIMBS = tuple(int(x) for x in os.environ.get("QB_LIMBS", "16,19,25,32,38,48").split(","))
@@ -108,7 +110,7 @@ def build_facade(force: bool = False, verbose: bool = True, engine_lib: str = LI
         obj = os.path.join(BUILD, f"{tag}.{src}.o")
         objs.append(obj)
         if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
-            todo.append(([CXX, "-std=c++17", "-O2", "-fPIC", "-pthread", "-w", "-I" + inc, "-c", os.path.join(HOST, src), "-o", obj],
+            todo.append(([CXX, "-std=c++17", "-O2", "-g", "-fPIC", "-pthread", "-w", "-I" + inc, "-c", os.path.join(HOST, src), "-o", obj],
                          os.path.join(BUILD, f"{tag}.{src}.log")))
     if todo or not os.path.exists(out) or os.path.getmtime(engine_lib) > os.path.getmtime(out):
         with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:

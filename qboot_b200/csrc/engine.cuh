@@ -138,7 +138,7 @@ namespace qb
 		Rational eps{0, 1};
 		ContextConsts<L> consts;
 		std::map<uint32_t, T> b0_cache;
-		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_qc, d_pv, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms, d_fb_g;
+		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_qc, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms, d_fb_g;
 		DevCtx cx{};
 		int n_tables = 0, n_jobs = 0;
 		bool tables_valid = false;  // a gblock_run has completed for the current plan
@@ -168,7 +168,7 @@ namespace qb
 		~Engine() override
 		{
 			cudaSetDevice(device);
-			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_qc, &d_pv, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
+			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_qc, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
 			                  &d_fb_terms, &d_fb_g})
 				b->release();
 			pmp_release();
@@ -426,7 +426,7 @@ namespace qb
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
-			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (2 * n1 + 1) * nt) || d_qc.ensure(sizeof(T) * nt) || d_pv.ensure(sizeof(T) * 8 * size_t(n_max) * nj) || d_a.ensure(sizeof(T) * a_slot_records) ||
+			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (2 * n1 + 1) * nt) || d_qc.ensure(sizeof(T) * nt) || d_a.ensure(sizeof(T) * a_slot_records) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;
 			t_delta = d_in.as<T>();
@@ -469,15 +469,9 @@ namespace qb
 			                     d_coef.as<T>() + size_t(r.j0) * QB_NCOEF, st);
 			++launches;
 		}
-		void stage_polyvals(const Range& r, cudaStream_t st)
-		{
-			launch_polyvals<L>(cx, r.j1 - r.j0, j_spin + r.j0, d_coef.as<T>() + size_t(r.j0) * QB_NCOEF,
-			                   d_pv.as<T>() + size_t(r.j0) * n_max * 8, st);
-			++launches;
-		}
 		void stage_series(const Range& r, cudaStream_t st)
 		{
-			launch_series<L>(cx, r.j1 - r.j0, j_delta + r.j0, j_spin + r.j0, j_b0 + r.j0, d_pv.as<T>() + size_t(r.j0) * n_max * 8,
+			launch_series<L>(cx, r.j1 - r.j0, j_delta + r.j0, j_spin + r.j0, j_b0 + r.j0, d_coef.as<T>() + size_t(r.j0) * QB_NCOEF,
 			                 d_b.as<T>() + size_t(r.j0) * (size_t(n_max) + 1), st);
 			++launches;
 		}
@@ -520,9 +514,8 @@ namespace qb
 			stage_rec(r, st);
 			if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
 			if (timed) QB_CU(cudaEventRecord(ev[1], st));
-			stage_polyvals(r, st);
 			stage_series(r, st);
-			if (int rc_ = debug_sync("k_polyvals/k_series")) return rc_;
+			if (int rc_ = debug_sync("k_series")) return rc_;
 			if (timed) QB_CU(cudaEventRecord(ev[2], st));
 			stage_pow(r, st);
 			stage_deriv(r, st);
@@ -601,7 +594,6 @@ namespace qb
 			{
 				const Range r = range_of(c);
 				stage_rec(r, lo_stream);
-				stage_polyvals(r, lo_stream);
 				QB_CU(cudaEventRecord(EV(c, 0), lo_stream));
 				cudaStream_t hs = hi_streams[size_t(c)];
 				stage_pow(r, hs);

@@ -1,7 +1,6 @@
 // qboot_b200 -- CUDA kernels of the block-table pipeline (sm_100a), templated on the limb count L; split by kernel
 // group so that each translation unit (kernel_inst.cu -DQB_KGROUP=g) only parses what it instantiates:
 //   kernels_g0.cuh  k_rec_coeffs  one thread per (series job, recurrence coefficient)              -> coef[job][40]
-//                   k_polyvals    one thread per (series job, n): the recurrence polynomials at n  -> pv[job][n][8]
 //                   k_ops         diagnostic: one primitive elementwise
 //   kernels_g1.cuh  k_series      one thread per series job, n_max sequential steps                -> b[job][0..n_max]
 //   kernels_g2.cuh  k_scale       one thread per (table, n): the lambda+1 scaled coefficient arrays -> a[table][k][n]
@@ -54,78 +53,6 @@ namespace qb
 		mpf<L> pe[5];
 		rec_coeffs_end(pe, lD, sp, cx.eps, cx.prec, i == 0);
 		for (int k = 0; k < st; ++k) copy(out[i * st + k], pe[k]);
-	}
-
-	// 64-bit record transfers (see kernels_g2.cuh): for even L every record of a 256-byte aligned array is 8-byte aligned
-	template <int L>
-	__device__ __forceinline__ void load_rec64(mpf<L>& d, const mpf<L>* src)
-	{
-		if constexpr (L % 2 == 0)
-		{
-			const uint2* sp = reinterpret_cast<const uint2*>(src);
-			uint2 v = sp[0];
-			d.sk = v.x;
-			d.exp = int32_t(v.y);
-#pragma unroll
-			for (int j = 0; j < L / 2; ++j)
-			{
-				v = sp[1 + j];
-				d.m[2 * j] = v.x;
-				d.m[2 * j + 1] = v.y;
-			}
-		}
-		else
-			copy(d, *src);
-	}
-	template <int L>
-	__device__ __forceinline__ void store_rec64(mpf<L>* dst, const mpf<L>& s)
-	{
-		if constexpr (L % 2 == 0)
-		{
-			uint2* dp = reinterpret_cast<uint2*>(dst);
-			dp[0] = make_uint2(s.sk, uint32_t(s.exp));
-#pragma unroll
-			for (int j = 0; j < L / 2; ++j) dp[1 + j] = make_uint2(s.m[2 * j], s.m[2 * j + 1]);
-		}
-		else
-			copy(*dst, s);
-	}
-
-	// values of the K recurrence polynomials at every n: pv[(job * n_max + n - 1) * 8 + i] = p_i(n), by Horner with the
-	// integer n (include/qboot/algebra/polynomial.hpp:66-83).  They do not depend on the series, so they are taken off its
-	// sequential chain: one thread per (job, n).
-	template <int L>
-	__global__ void k_polyvals(DevCtx cx, int n_jobs, const uint32_t* __restrict__ spin, const mpf<L>* __restrict__ coef,
-	                           mpf<L>* __restrict__ pv)
-	{
-		const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-		const int job = int(gid / cx.n_max);
-		const uint32_t n = uint32_t(gid % cx.n_max) + 1u;
-		if (job >= n_jobs) return;
-		const uint32_t sp = spin[job];
-		int K = sp == 0 ? 6 : 8, deg = sp == 0 ? 3 : 4;
-#ifdef __CUDA_ARCH__
-		// keep ONE copy of the loop body: without this the compiler clones and unrolls it per spin class and the kernel
-		// outgrows the instruction cache (measured: 75 % of its stall samples were instruction fetch)
-		asm volatile("" : "+r"(K), "+r"(deg));
-#endif
-		const int st = deg + 1;
-		const mpf<L>* c = coef + size_t(job) * QB_NCOEF;
-		mpf<L>* out = pv + size_t(gid) * 8;
-		QB_ROLL
-		for (int i = 0; i < K; ++i)
-		{
-			mpf<L> s, cd;
-			load_rec64(s, &c[i * st + deg]);
-			QB_ROLL
-			for (int d = deg - 1; d >= 0; --d)
-			{
-				fast::mul_small(s, s, int64_t(n), cx.prec);
-				load_rec64(cd, &c[i * st + d]);
-				fast::add(s, s, cd, cx.prec);
-			}
-			store_rec64(&out[i], s);
-		}
 	}
 
 	// Elementwise primitive (diagnostic entry qb_op_batch): lets the GPU test-suite pin the device build of every

@@ -42,10 +42,8 @@ namespace qb
 	void launch_rec_coeffs(const DevCtx& cx, int n_jobs, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* S,
 	                       const mpf<L>* P, mpf<L>* coef, cudaStream_t st);
 	template <int L>
-	void launch_polyvals(const DevCtx& cx, int n_jobs, const uint32_t* spin, const mpf<L>* coef, mpf<L>* pv, cudaStream_t st);
-	template <int L>
 	void launch_series(const DevCtx& cx, int n_jobs, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* b0,
-	                   const mpf<L>* pv, mpf<L>* b, cudaStream_t st);
+	                   const mpf<L>* coef, mpf<L>* b, cudaStream_t st);
 	template <int L>
 	void launch_scale(const DevCtx& cx, int n_tables, const TableRef* tref, const mpf<L>* b, const mpf<L>* pw, mpf<L>* a,
 	                  cudaStream_t st);

@@ -238,3 +238,76 @@ def test_bench_workload_vs_reference(ref):
     want = ref.gblock(prec, n_max, lam, "3", delta, spin, S, P)
     bad = [i for i in range(len(keys)) if not np.array_equal(got[i], want[i])]
     assert len(keys) >= 80 and not bad, bad
+
+
+# ---- the PMP half of the path: planner + device assembly / pack / decimal text through the C++ facade -------------------
+def _same_dirs(a, b):
+    import filecmp
+    import os
+
+    fa, fb = sorted(os.listdir(a)), sorted(os.listdir(b))
+    assert fa == fb
+    return [f for f in fa if not filecmp.cmp(os.path.join(a, f), os.path.join(b, f), shallow=False)]
+
+
+@pytest.mark.parametrize("prec,n_max,lam,model,mode,finite,numax,maxspin", [
+    (600, 100, 11, 0, 0, True, 8, 24),      # BASELINE config 1: single-correlator Ising, 600-bit, spins 0-24 + finite range
+    (800, 200, 13, 1, 1, True, 10, 30),     # BASELINE config 2: mixed Ising, Delta12 != 0 blocks, finite ranges [lb, ub), 800-bit
+    (1000, 120, 10, 1, 0, False, 6, 12),    # FindContradiction on the mixed system, 1000 bits (not a limb multiple)
+])
+def test_sdpb_directory_equals_reference(ref, tmp_path, prec, n_max, lam, model, mode, finite, numax, maxspin):
+    """convert -> create_input -> write on the GPU engine vs the reference's MPFR build: every file byte for byte"""
+    want, got = str(tmp_path / "ref"), str(tmp_path / "ours")
+    r = ref.build_pmp(prec, n_max, lam, "3", model, mode, finite, numax=numax, maxspin=maxspin, threads=8, outdir=want)
+    o = qb.build_pmp(prec, n_max, lam, "3", model, mode, finite, numax=numax, maxspin=maxspin, threads=8, outdir=got)
+    assert o["constraints"] == r["constraints"] and o["N"] == r["N"]
+    assert _same_dirs(got, want) == []
+
+
+def test_device_decimal_text_vs_reference(ref):
+    """k_dec_format against the reference's ostream (mpfr_get_str digits + default-float layout) at the SDPB digit count"""
+    import ctypes as C
+
+    from tests.golden.make_golden import rnd_num
+    from tests.util import P
+
+    for prec in (600, 1024, 1536):
+        eng = _engine(prec, 20, 5)
+        rng = random.Random(prec)
+        nd = 3 + int(prec * 0.302)
+        vals = [rnd_num(rng, prec, -500, 500) for _ in range(300)]  # |x| < 10^151 < 10^nd: inside the device formatter's range
+        vals += [ref.from_str(s, prec) for s in ["1", "0.5", "10", "1000", "999999", "1e-5", "0.001", "0.0001", "-2", "123.456", "0.1", "0"]]
+        vals.append(ref.op("add", prec, a=ref.from_str("0.5", prec), b=ref.from_int_exp(0, 1, -(nd + 1), prec))[0])  # a tie
+        vals += [ref.from_str("1e1500", prec), ref.from_str("-3e-2000", prec)]  # outside the device range: declined
+        x = np.stack(vals)
+        slot = nd + 16
+        slots = np.zeros((len(x), slot), dtype=np.uint8)
+        ln = np.zeros(len(x), dtype=np.int32)
+        eng._check(eng.lib.qb_dec_format(eng.h, nd, len(x), P(x), P(slots), slot, P(ln)), "qb_dec_format")
+        declined = 0
+        for i, v in enumerate(x):
+            if ln[i] < 0:
+                declined += 1
+                continue
+            assert slots[i, : ln[i]].tobytes().decode() == ref.to_str(v, prec, nd) + "\n", ref.to_str(v, prec, 20)
+        assert declined == 2
+        eng.close()
+
+
+def test_facade_single_calls_vs_reference(ref):
+    """Context::gBlock / evaluate through the facade's one-table path equal the batched engine results (smoke of the API)"""
+    prec, n_max, lam = 600, 60, 9
+    eng = _engine(prec, n_max, lam)
+    d = qb.from_str("1.7", prec)
+    z = qb.from_fraction(0, prec)
+    t = eng.gblock([2], d, z, z)
+    assert np.array_equal(t, ref.gblock(prec, n_max, lam, "3", d, [2], z, z))
+    dv = np.stack([qb.from_str("0.5181489", prec)])
+    out = np.zeros((1, eng.dim_M, eng.W), dtype=np.uint32)
+    from tests.util import P
+    eng._check(eng.lib.qb_vtod_batch(eng.h, 1, P(dv), P(out)), "qb_vtod_batch")
+    fb = np.zeros((qb.load_library().qb_block_dim(eng.h, 1), eng.W), dtype=np.uint32)
+    sym = np.array([1], dtype=np.int32)
+    eng._check(eng.lib.qb_fblock_tables(eng.h, 1, P(np.ascontiguousarray(t[0])), P(dv), P(sym), P(fb)), "qb_fblock_tables")
+    assert np.array_equal(fb, ref.fblock(prec, n_max, lam, "3", dv[0], d, 2, z, z, 1))
+    eng.close()
