@@ -1,31 +1,36 @@
 #!/usr/bin/env python
-"""Benchmark of qboot's block-table hot path on B200 (BASELINE.json metric: gBlock tables/s at lambda = 19,
-n_Max = 400, 1024-bit; the PMP-build leg is reported once the PMP assembly rows are built).
+"""Benchmark of qboot's data-parallel hot path on B200 -- BASELINE.json metric: "gBlock tables/s (lambda = 19,
+n_Max = 400, 1024-bit) + full PMP build time vs CPU".
 
-  python bench.py --gpus N --steps K --warmup W            this engine (CUDA, through the C ABI)
+  python bench.py --gpus N --steps K --warmup W            this engine (CUDA, through the C ABI / the C++ facade)
   python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU implementation (oracle/_ref)
 
-A "step" is one pass of the hot path over one batch of synthetic block-table keys: the scan workload of BASELINE
-config 5 -- the mixed-correlator Ising key set (spins 0..50, numax = 20, three (S, P) classes) repeated over a grid of
-(Delta_sigma, Delta_epsilon) -- `tables_per_gpu` tables per GPU per step (weak scaling: every rank gets its own shard
-of the grid, there is no data-path collective; rank 0 gathers the timings).
-
-  value     tables/s with the inputs already resident in HBM (qb_gblock_plan done; qb_gblock_run timed with CUDA
-            events on the launching stream; barrier + synchronize on both sides; max over ranks)
+M1 -- block tables per second.  A "step" is one pass of the table pipeline over the scan workload of BASELINE config 5:
+the mixed-correlator Ising key set (spins 0..50, numax = 20, three (S, P) classes) repeated over a grid of
+(Delta_sigma, Delta_epsilon); --total-tables keys per step IN TOTAL, dealt round-robin by cost class (spin 0 / spin > 0)
+to the ranks: STRONG scaling.  With N > 1 every step ends with the gather of all tables into rank 0's HBM over
+NVLink (NCCL grouped send/recv through torch.distributed), inside the timed region.
+  value     tables/s, inputs resident in HBM (qb_gblock_plan done; qb_gblock_run [+ gather] timed with CUDA events on the
+            launching stream; barrier + synchronize on both sides; max over ranks)
   e2e       tables/s through qb_gblock_batch with HOST buffers in and out (planning, H2D, kernels, D2H all timed)
-  roofline  the dominant stage (rho-derivative chains: k_scale + k_horner) against the MEASURED limb-product rate of
-            this GPU (qb_imad_peak, IMAD.WIDE.U32); the path is multiply-bound (>= 8 MAC per HBM byte against a machine
-            balance of ~1), so the bound is "imad", not hbm/tensor; `traffic` = ncu dram bytes of that stage per launch
-  cpu_baseline  oracle/_ref (the unmodified reference, MPFR) on this box's host cores, bounded sample, rank 0, N = 1
-  parity_check  (with cpu_baseline, untimed) 64 tables of the end-to-end leg's output against the reference, word for word
+  roofline  whole step against the MEASURED limb-product rate of this GPU (qb_imad_peak, IMAD.WIDE.U32): the path is
+            multiply-bound (>= 8 MAC per HBM byte against a machine balance of ~1), so the bound is "imad", not
+            hbm/tensor; per-stage fractions in `stages`; `traffic` = ncu dram bytes of the dominant stage per launch
+  cpu_baseline  oracle/_ref (the unmodified reference, MPFR) on this box's host cores, bounded strided sample, rank 0, N = 1
+M2 -- full PMP build (convert -> create_input -> write), N = 1 only: `pmp_build` holds wall seconds per phase of the
+  single-correlator (1 289 tables) and mixed-correlator (6 254 tables, 407 MB of SDPB text) north-star builds through the
+  C++ facade (qboot::Context ... SDPBInput::write on the GPU engine), beside the reference's own build of the same
+  model on all host cores, and whether the two directories are byte-identical.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -37,7 +42,9 @@ sys.path.insert(0, ROOT)
 PREC, N_MAX, LAM, DIM, NUMAX, MAXSPIN = 1024, 400, 19, "3", 20, 50
 METRIC = "gblock_tables_per_s"
 UNIT = "tables/s"
-WORKLOAD = "gBlock tables, Context(n_Max=400, lambda=19, dim=3), 1024-bit, mixed-Ising key set (spins 0-50, numax=20) swept over a (Delta_sigma, Delta_epsilon) grid"
+WORKLOAD = ("gBlock tables, Context(n_Max=400, lambda=19, dim=3), 1024-bit, mixed-Ising key set (spins 0-50, numax=20) swept over a "
+            "(Delta_sigma, Delta_epsilon) grid; N = 1 also: full PMP build of the single- and mixed-correlator Ising problems")
+TOTAL_TABLES = 392768  # 8 x 49 096: 64 grid points of the 13 x 13 scan (a fixed total for every N: strong scaling)
 
 
 def host_cores() -> int:
@@ -78,11 +85,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_shard(rank: int, tables: int):
-    """rank-specific slice of the scan workload (deterministic)"""
+def make_shard(rank: int, world: int, total: int):
+    """this rank's share of the scan workload (deterministic): the keys of `total` tables, sorted by cost class
+    (spin 0 tables run a shorter recurrence than spin > 0) and dealt round-robin -- SURVEY section 8(e)"""
     from qboot_b200 import workload as wl
 
-    keys = wl.sweep_keys(PREC, LAM, NUMAX, MAXSPIN, tables * (rank + 1))[tables * rank:]
+    keys = wl.sweep_keys(PREC, LAM, NUMAX, MAXSPIN, total)
+    if world > 1:
+        order = sorted(range(len(keys)), key=lambda i: (keys[i][0] != 0, i))
+        keys = [keys[i] for i in order[rank::world]]
     return wl.to_records(keys, PREC)
 
 
@@ -93,6 +104,10 @@ def total_work(spin, stage="total"):
     w1 = wl.work_per_table(N_MAX, LAM, 32, 1)[stage]
     n0 = int((spin == 0).sum())
     return n0 * w0 + (len(spin) - n0) * w1
+
+
+def strided_sample(n: int, count: int):
+    return np.arange(0, n, max(1, n // count))[:count]
 
 
 def run_reference(args, rank, world):
@@ -106,34 +121,97 @@ def run_reference(args, rank, world):
         return 0
     cores = host_cores()
     sample = int(args.ref_tables) if args.ref_tables else max(64, 16 * cores)
-    spin, delta, S, P = make_shard(0, sample)
+    spin, delta, S, P = make_shard(0, 1, 49096)
+    idx = strided_sample(len(spin), sample)  # every sector, spin and (S, P) class of the key set
+    spin, delta, S, P = spin[idx], delta[idx], S[idx], P[idx]
     for _ in range(args.warmup):
         ref.time_gblock(PREC, N_MAX, LAM, DIM, delta[:cores], spin[:cores], S[:cores], P[:cores], cores)
     t = 0.0
     for _ in range(args.steps):
         t += ref.time_gblock(PREC, N_MAX, LAM, DIM, delta, spin, S, P, cores)
-    value = sample * args.steps / t
+    value = len(idx) * args.steps / t
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "mpfr-1024 (f1024)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tables_per_step": sample},
+        "config": {"workload": WORKLOAD, "tables_per_step": int(len(idx))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": f"{sample} tables per step through qboot::gBlock on {cores} host threads (reference task fan-out)"},
+                         "sample": f"{len(idx)} tables per step, strided over the whole key set, through qboot::gBlock on {cores} host threads (reference task fan-out)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_pmp:
+        line["pmp_build"] = {"single": ref_pmp(0, cores), "mixed": ref_pmp(1, cores)}
     print(json.dumps(line))
     return 0
+
+
+def ref_pmp(model: int, cores: int, outdir=None):
+    from oracle import ref
+
+    d = outdir or tempfile.mkdtemp(prefix="qb_ref_pmp_")
+    t = time.perf_counter()
+    r = ref.build_pmp(PREC, N_MAX, LAM, DIM, model, 1 if model else 0, True, numax=NUMAX, maxspin=MAXSPIN, threads=cores, outdir=d)
+    r["wall_s"] = time.perf_counter() - t
+    r["threads"] = cores
+    if outdir is None:
+        shutil.rmtree(d, ignore_errors=True)
+    return r
+
+
+def pmp_leg(cores: int, with_reference: bool):
+    """M2: convert -> create_input -> write through the C++ facade, cold and warm, beside the reference on this box"""
+    import filecmp
+
+    import qboot_b200 as qb
+
+    out = {}
+    for name, model in (("single", 0), ("mixed", 1)):
+        root = tempfile.mkdtemp(prefix="qb_pmp_")
+        runs = []
+        for rep in range(3):
+            d = os.path.join(root, f"ours{rep}")
+            t = time.perf_counter()
+            r = qb.build_pmp(PREC, N_MAX, LAM, DIM, model, 1 if model else 0, True, numax=NUMAX, maxspin=MAXSPIN, threads=cores, outdir=d)
+            r["wall_s"] = time.perf_counter() - t
+            runs.append(r)
+        best = min(runs[1:], key=lambda r: r["wall_s"])
+        rec = {"wall_s": best["wall_s"], "convert_s": best["convert"], "create_input_s": best["create_input"], "write_s": best["write"],
+               "first_call_wall_s": runs[0]["wall_s"], "constraints": best["constraints"], "N": best["N"],
+               "sdpb_bytes": sum(os.path.getsize(os.path.join(root, "ours1", f)) for f in os.listdir(os.path.join(root, "ours1"))),
+               "host_threads": cores}
+        if with_reference:
+            rd = os.path.join(root, "ref")
+            rr = ref_pmp(model, cores, rd)
+            files = sorted(os.listdir(rd))
+            differing = [f for f in files if not filecmp.cmp(os.path.join(rd, f), os.path.join(root, "ours1", f), shallow=False)]
+            rec["reference"] = {"wall_s": rr["wall_s"], "convert_s": rr["convert"], "create_input_s": rr["create_input"], "write_s": rr["write"],
+                                "tables": rr["tables"], "threads": cores, "kind": "unmodified reference (oracle/_ref), all host cores"}
+            rec["tables"] = rr["tables"]
+            rec["files"] = len(files)
+            rec["byte_identical_to_reference"] = (differing == [] and sorted(os.listdir(os.path.join(root, "ours1"))) == files)
+            rec["speedup_vs_reference"] = rr["wall_s"] / best["wall_s"]
+        shutil.rmtree(root, ignore_errors=True)
+        out[name] = rec
+    return out
 
 
 def ncu_traffic(n_tables):
     """DRAM bytes per launch of the dominant stage from the committed ncu --set full capture (profiles/), scaled from the
     captured launch's table count to this run's chunk size; None when no capture is recorded."""
-    try:
-        rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
-        return rec["deriv_dram_bytes_per_table"] * min(n_tables, rec.get("chunk_tables", n_tables))
-    except Exception:
-        return None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return rec["deriv_dram_bytes_per_table"] * min(n_tables, rec.get("chunk_tables", n_tables))
+        except Exception:
+            continue
+    return None
+
+
+class _DevBytes:
+    """a raw device allocation of the engine as something torch can wrap (no copy)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
 
 
 def main():
@@ -142,9 +220,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tables-per-gpu", type=int, default=int(os.environ.get("QB_BENCH_TABLES", "49096")))
+    ap.add_argument("--total-tables", type=int, default=int(os.environ.get("QB_BENCH_TABLES", str(TOTAL_TABLES))))
     ap.add_argument("--ref-tables", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pmp", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rules: at least 3 warm-up steps
@@ -168,9 +247,11 @@ def main():
 
     eng = qb.Engine(PREC, device=local).context(N_MAX, LAM, DIM)
     stream = torch.cuda.ExternalStream(eng.stream, device=local)
-    n = args.tables_per_gpu
-    spin, delta, S, P = make_shard(rank, n)
+    total = args.total_tables - args.total_tables % world
+    spin, delta, S, P = make_shard(rank, world, total)
+    n = len(spin)
     W = eng.W
+    table_bytes = eng.dim_M * W * 4
     # pinned host staging for the end-to-end leg
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
     h_spin, h_delta, h_S, h_P = pin(spin.astype(np.uint32).view(np.int32)), pin(delta.view(np.int32)), pin(S.view(np.int32)), pin(P.view(np.int32))
@@ -185,8 +266,26 @@ def main():
     eng.plan(spin, delta, S, P)
     peak = eng.imad_peak(4096)
     eng.set_timing(False)
-    for _ in range(args.warmup):
+    gathered = None
+    if world > 1:
+        # rank 0 receives every rank's tables (its own included) into one buffer in its HBM
+        mine = torch.as_tensor(_DevBytes(eng.lib.qb_gblock_device_tables(eng.h), n * table_bytes), device=f"cuda:{local}")
+        gathered = [torch.empty(n * table_bytes, dtype=torch.uint8, device=f"cuda:{local}") for _ in range(world)] if rank == 0 else None
+
+    gev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (args.steps + args.warmup))]
+
+    def step(i):
+        # all kernels over the resident shard (chunks spread over the engine's streams, joined on the handle's stream), then
+        # the gather on the same stream: NCCL waits for the tables and the stream waits for NCCL, no host synchronisation
         eng.run()
+        if world > 1:
+            with torch.cuda.stream(stream):
+                gev[2 * i].record(stream)
+                dist.gather(mine, gathered, dst=0)
+                gev[2 * i + 1].record(stream)
+
+    for i in range(args.warmup):
+        step(i)
     eng.sync()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -197,20 +296,22 @@ def main():
     t_wall = time.perf_counter()
     with torch.cuda.stream(stream):
         ev0.record(stream)
-    for _ in range(args.steps):
-        # one step = all kernels over the resident batch (chunks round-robin over the engine's streams and join on the
-        # handle's stream).  Every step rewrites its tables, series and scaled-coefficient arrays (several GB, > L2).
-        eng.run()
+    for i in range(args.steps):
+        # every step rewrites its tables, series and scaled-coefficient arrays (tens of GB, far beyond the 126 MB L2)
+        step(args.warmup + i)
     with torch.cuda.stream(stream):
         ev1.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches_timed = eng.launches - launches_before
     dev_ms = ev0.elapsed_time(ev1)
+    gather_ms = 0.0
+    if world > 1:
+        gather_ms = sum(gev[2 * (args.warmup + i)].elapsed_time(gev[2 * (args.warmup + i) + 1]) for i in range(args.steps)) / args.steps
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-kernel device times (CUDA events on the launching stream around every kernel; chunks run back to back on one
-    # stream in this mode so that the events bracket exactly one kernel each)
+    # per-kernel device times (CUDA events on the launching stream around every stage; chunks run back to back on one
+    # stream in this mode so that the events bracket exactly one stage each)
     eng.set_timing(True)
     kms = np.zeros(4)
     ksteps = max(1, min(args.steps, 2))
@@ -219,7 +320,7 @@ def main():
     for _ in range(ksteps):
         eng.run()
         kms += np.array(eng.kernel_times())
-    kms *= args.steps / ksteps  # scaled so that kms / steps below is the per-step mean
+    kms /= ksteps  # per step
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the one-shot C-ABI call ------------------------------
     lib, h = eng.lib, eng.h
@@ -242,13 +343,13 @@ def main():
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------------------
-    stats = torch.tensor([dev_ms, e2e_s, kms[2] / args.steps, float(n)], dtype=torch.float64, device=f"cuda:{local}")
+    stats = torch.tensor([dev_ms, e2e_s, gather_ms, float(n)], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s, total_tables = float(mx[0]), float(mx[1]), float(sm[3])
+        dev_ms, e2e_s, gather_ms, total_tables = float(mx[0]), float(mx[1]), float(mx[2]), float(sm[3])
     else:
         total_tables = float(n)
     if rank != 0:
@@ -258,30 +359,39 @@ def main():
 
     ms_per_step = dev_ms / args.steps
     value = total_tables / (ms_per_step * 1e-3)
-    deriv_ms = kms[2] / args.steps
-    w_deriv = total_work(spin, "deriv")
-    achieved = w_deriv / (deriv_ms * 1e-3)
     in_bytes = int(spin.nbytes + delta.nbytes + S.nbytes + P.nbytes)
-    out_bytes = int(n * eng.dim_M * W * 4)
+    out_bytes = int(n * table_bytes)
+    stage_names = ("rec", "series", "deriv", "finish")
+    stages = {}
+    for i, s in enumerate(stage_names):
+        w = total_work(spin, s)
+        stages[s] = {"ms_per_step": float(kms[i]), "limb_macs": float(w), "frac_of_peak": float(w / (kms[i] * 1e-3) / peak) if kms[i] > 0 else None}
+    step_frac = total_work(spin) * world / (ms_per_step * 1e-3) / (peak * world)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f1024 (32 x u32 limbs, round-to-nearest-even per operation)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tables_per_gpu_per_step": n, "precision_bits": PREC, "n_Max": N_MAX, "lambda": LAM,
+        "config": {"workload": WORKLOAD, "total_tables_per_step": int(total_tables), "tables_per_gpu_per_step": n, "precision_bits": PREC,
+                   "n_Max": N_MAX, "lambda": LAM, "sharding": "keys sorted by cost class (spin 0 / spin > 0), dealt round-robin to the ranks",
                    "l2": "each step rewrites its %d MB of tables and %d MB of series coefficients (> 126 MB L2)" % (
                        out_bytes // 2**20, n * (N_MAX + 1) * W * 4 // 2**20)},
         "e2e": {"value": total_tables / e2e_s, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes},
         "gpu_launches": int(launches_timed),
-        "kernel_ms_per_step": {"rec_coeffs": kms[0] / args.steps, "series": kms[1] / args.steps, "deriv": deriv_ms,
-                               "finish": kms[3] / args.steps},
-        "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlimb-MAC/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(n), "kernel": "k_scale + k_horner (rho-derivative chains, stage a4)",
-                     "whole_step_frac": total_work(spin) / (ms_per_step * 1e-3) / peak,
+        "kernel_ms_per_step": {"rec_coeffs": float(kms[0]), "series": float(kms[1]), "deriv": float(kms[2]), "finish": float(kms[3]),
+                               "note": "chunks serialised on one stream with an event around every stage; the timed step overlaps them"},
+        "roofline": {"bound": "imad", "achieved": step_frac * peak / 1e12, "peak": peak / 1e12, "unit": "Tlimb-MAC/s", "frac": step_frac,
+                     "traffic": ncu_traffic(n), "kernel": "whole step (k_rec_coeffs, k_series, k_pow, k_scale, k_horner, k_rho_to_z, k_offdiag_*)",
+                     "stages": stages,
                      "peak_source": "measured on this GPU by qb_imad_peak: dependency-free IMAD.WIDE.U32 chains at full occupancy "
                                     "(32 x 32 + 64 -> 64; issues at 32 per clock per SM, half the 32-bit IMAD rate)",
-                     "hbm_gbs_achieved": (out_bytes + n * (N_MAX + 1) * W * 4 * 2) / (ms_per_step * 1e-3) / 1e9},
+                     "work": "algorithmic limb-MACs of the reference algorithm per table (SURVEY 8(d)): mul/fma L^2, div 2 L^2, pow 64 L^2"},
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }
+    if world > 1:
+        nv = int((world - 1) * n * table_bytes)
+        line["gather"] = {"ms_per_step": gather_ms, "nvlink_bytes_per_step": nv, "to": "rank 0 HBM",
+                          "how": "torch.distributed.gather over NCCL (grouped send/recv), enqueued behind the tables on the engine's stream",
+                          "gbytes_per_s": (nv / 1e9) / (gather_ms * 1e-3) if gather_ms > 0 else None}
     if world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import ref
@@ -289,17 +399,30 @@ def main():
             if ref.available():
                 cores = host_cores()
                 sample = max(64, 16 * cores)
-                t = ref.time_gblock(PREC, N_MAX, LAM, DIM, delta[:sample], spin[:sample], S[:sample], P[:sample], cores)
-                line["cpu_baseline"] = {"value": sample / t, "unit": UNIT, "cores": cores, "kind": "reference",
-                                        "sample": f"first {sample} tables of the same workload through the unmodified reference (qboot::gBlock, MPFR 4.2.1) on {cores} host threads"}
+                idx = strided_sample(n, sample)
+                t = ref.time_gblock(PREC, N_MAX, LAM, DIM, delta[idx], spin[idx], S[idx], P[idx], cores)
+                line["cpu_baseline"] = {"value": len(idx) / t, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"{len(idx)} tables strided over the same workload (all sectors, spins and (S, P) classes) through the "
+                                                  f"unmodified reference (qboot::gBlock, MPFR 4.2.1) on {cores} host threads"}
                 # not timed: the tables the end-to-end leg just wrote to host memory, against the reference's, word for word
-                idx = np.arange(0, n, max(1, n // 64))[:64]
+                idx = strided_sample(n, 256)
                 want = ref.gblock(PREC, N_MAX, LAM, DIM, delta[idx], spin[idx], S[idx], P[idx])
                 got = h_out.numpy().view(np.uint32)[idx]
                 line["parity_check"] = {"tables": int(len(idx)), "bit_identical": bool(np.array_equal(got, want)),
                                         "against": "unmodified reference (oracle/_ref) on the same keys"}
         except Exception as ex:  # the baseline is reported, never required
             line["cpu_baseline"] = {"error": str(ex)}
+    if world == 1 and not args.no_pmp:
+        # M2.  The table engine's buffers are released first: the facade owns its own handle
+        del h_out
+        eng.close()
+        torch.cuda.empty_cache()
+        try:
+            from oracle import ref
+
+            line["pmp_build"] = pmp_leg(host_cores(), ref.available() and not args.no_cpu_baseline)
+        except Exception as ex:
+            line["pmp_build"] = {"error": str(ex)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -292,6 +292,12 @@ namespace qboot
 		[[nodiscard]] PolynomialProgram convert(const std::unique_ptr<SDPMode>& mode, uint32_t parallel = 1,
 		                                        const std::unique_ptr<_event_base>& event = {}) const;
 		[[nodiscard]] algebra::Vector<mp::real> recover(const std::unique_ptr<SDPMode>& mode, const algebra::Vector<mp::real>& raw_func) const;
+		// Extremal functional method (src/bootstrap_equation.cpp:463-542).  Post-processing of an SDPB solution by exact
+		// rational root isolation: outside the scope of this engine.  Declared so that drivers written
+		// for the reference compile; calling it throws std::logic_error.
+		std::map<std::string, std::vector<PrimaryOperator>, std::less<>> get_spectrum(const algebra::Vector<mp::real>& recovered_func,
+		                                                                              uint32_t parallel = 1,
+		                                                                              const std::unique_ptr<_event_base>& event = {}) const;
 	};
 	using Externals = std::array<PrimaryOperator, 4>;
 	// one crossing equation: terms per sector, all of one symmetry (Odd = F-type, Even = H-type)

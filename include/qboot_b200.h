@@ -187,7 +187,7 @@ int qb_pmp_text_fetch(qb_handle* h, char* out);
 /* out[0] blocks in the arena, [1] N, [2] records in the arena, [3] selected blocks of the last pack */
 int qb_pmp_info(const qb_handle* h, int64_t* out4);
 /* Diagnostic: n numbers (HOST) formatted on the device into slots of `slot` >= ndigits + 16 bytes; len[i] = bytes used
- * or -1 when declined. */
+ * or a negative code when declined (see format_decimal in qboot_b200/csrc/pmp.cuh). */
 int qb_dec_format(qb_handle* h, int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* len);
 
 #ifdef __cplusplus

@@ -75,7 +75,7 @@ namespace qb
 			copy(Carena[blk.ofs_c + p], r);
 	}
 
-	// numbers -> text slots of `slot` bytes each; len[i] = bytes used, or -1 when the host has to format number i
+	// numbers -> text slots of `slot` bytes each; len[i] = bytes used, or < 0 when the host has to format number i
 	template <int L>
 	__global__ void k_dec_format(DecTables tb, int64_t n, const mpf<L>* __restrict__ x, char* __restrict__ slots, int slot,
 	                             int32_t* __restrict__ len)

@@ -5,7 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "hor.cuh"
-#include "pmp.cuh"
+#include "pmp_types.cuh"
 
 namespace qb
 {

@@ -13,30 +13,10 @@
 #include <math.h>
 
 #include "block.cuh"
+#include "pmp_types.cuh"
 
 namespace qb
 {
-	// a term of a crossing equation inside one constraint block (host builds these, see include/qboot_b200.h)
-	struct PmpTerm
-	{
-		int32_t eq;    // equation index
-		int32_t rc;    // packed lower-triangle position r (r + 1) / 2 + c, c <= r
-		int32_t tab0;  // table of sample k: tab[tab0 + k]
-		int32_t d;     // index of the v-power table
-		int32_t coef;  // index of the coefficient record (already divided by 2 off the diagonal), < 0: coefficient 1
-	};
-	struct PmpBlock
-	{
-		int32_t n_samples, sz, term0, n_terms;
-		int64_t ofs;      // first record of M in the arena; M[p][n], p = rc * n_samples + k
-		int64_t thread0;  // first thread of this block in the assembly grid (n_rc * N * n_samples threads)
-		int64_t pack0;    // first thread of this block in the pack grid (schur * (n_free + 1) threads)
-		int64_t ofs_b;    // first record of d_B in its arena (schur x n_free, row-major)
-		int64_t ofs_c;    // first record of d_c in its arena (schur)
-		int64_t ofs_t;    // first record of the target values (schur), < 0: zero target
-	};
-	QB_HD QB_INLINE int pmp_schur(const PmpBlock& b) { return b.n_samples * (b.sz * (b.sz + 1) / 2); }
-
 	// (M, N) of the i-th kept entry of a block of parity sym, N-major / M-minor (complex_function.hpp:72-81)
 	QB_HD QB_INLINE void cf_decode_sym(int lambda, int sym, int i, int& M, int& N)
 	{
@@ -110,18 +90,6 @@ namespace qb
 	}
 
 	// ---- decimal text ---------------------------------------------------------------------------------------------------
-	// Tables for format_decimal, built on the host for one (L, ndigits): powers of five in two levels
-	//   5^k = P13[k / 13] * 5^(k % 13),  P13[a] = 5^(13 a) as little-endian limbs (length plen[a], offset pofs[a])
-	// and the bounds 10^ndigits, 10^(ndigits-1) as L + 2 limbs.
-	constexpr int QB_DEC_MAXA = 64;  // 5^(13 * 63): covers k <= 831
-	struct DecTables
-	{
-		const uint32_t* p13;       // concatenated limbs of 5^(13 a)
-		int32_t pofs[QB_DEC_MAXA + 1];
-		int ndigits;
-		const uint32_t* ten_n;     // 10^ndigits,     L + 2 limbs
-		const uint32_t* ten_n1;    // 10^(ndigits-1), L + 2 limbs
-	};
 	QB_HD QB_INLINE uint32_t pow5_small(int b)
 	{
 		uint32_t r = 1;
@@ -139,8 +107,9 @@ namespace qb
 		if (double(f) > v) --f;
 		return f + 1;
 	}
-	// out: sign, digits, point / exponent, '\n'.  Returns the length, or -1 when the number is outside the range handled
-	// here (huge or tiny exponents; the host formats those).  ND = ndigits <= 9 * NCH.
+	// out: sign, digits, point / exponent, '\n'.  Returns the length, or a negative code when the number is outside the range
+	// handled here (huge or tiny exponents; the host formats those): -1 digit count, -2 inf/nan, -3 exponent search did not
+	// settle, -4 |x| >= 10^ndigits or the power of five is beyond the table, -5 / -6 / -7 the scaled integer does not fit.
 	template <int L>
 	QB_HD QB_NOINLINE int format_decimal(char* out, const mpf<L>& x, const DecTables& tb)
 	{
@@ -157,21 +126,21 @@ namespace qb
 			out[len++] = '\n';
 			return len;
 		}
-		if (kind(x) != K_REG) return -1;
+		if (kind(x) != K_REG) return -2;
 		int d = dec_exponent_guess(x);
 		uint32_t Nn[NW];
 		for (int attempt = 0;; ++attempt)
 		{
-			if (attempt == 3) return -1;
+			if (attempt == 3) return -3;
 			const int k = n - d;
-			if (k < 0 || k / 13 >= QB_DEC_MAXA) return -1;
+			if (k < 0 || k / 13 >= QB_DEC_MAXA) return -4;
 			// N = RN(M * 5^k * 2^k / 2^(32 L - exp)) = RN((M * 5^k) >> s)
 			const int64_t s = int64_t(32) * L - int64_t(x.exp) - k;
-			if (s < 1) return -1;
+			if (s < 1) return -5;
 			const int a = k / 13, b = k % 13;
 			const uint32_t* P = tb.p13 + tb.pofs[a];
 			const int pl = tb.pofs[a + 1] - tb.pofs[a];
-			if (L + pl + 1 > PW) return -1;
+			if (L + pl + 1 > PW) return -6;
 			uint32_t prod[PW + 1];
 			const int tl = L + pl + 1;  // limbs in use
 			for (int i = 0; i < tl; ++i) prod[i] = 0u;
@@ -204,7 +173,7 @@ namespace qb
 			}
 			// shift right by s with round bit and sticky
 			const int q = int(s >> 5), r = int(s & 31);
-			if (q >= tl + 1) return -1;
+			if (q >= tl + 1) return -7;
 			// bit s - 1 is the round bit, everything below it is sticky
 			const int64_t rb = s - 1;
 			const int rq = int(rb >> 5), rr = int(rb & 31);

@@ -321,6 +321,11 @@ namespace qboot
 		assert(N_ > 0);
 		return mode->_prepare(N_, *this).recover(raw_func);
 	}
+	std::map<std::string, std::vector<PrimaryOperator>, std::less<>> BootstrapEquation::get_spectrum(const Vector<real>&, uint32_t,
+	                                                                                               const unique_ptr<_event_base>&) const
+	{
+		throw std::logic_error("qboot_b200: get_spectrum (extremal functional method) is outside the scope of this engine");
+	}
 	// src/bootstrap_equation.cpp:555-593, batched
 	PolynomialProgram BootstrapEquation::convert(const unique_ptr<SDPMode>& mode, uint32_t parallel, const unique_ptr<_event_base>& event) const
 	{

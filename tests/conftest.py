@@ -30,7 +30,7 @@ def hostemu():
 def _build_host_lib(out, srcs, deps, extra=()):
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-I" + os.path.join(ROOT, "include"), "-o", out, *srcs, *extra])
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-I" + os.path.join(ROOT, "include"), "-o", out, *srcs, *extra])
 
 
 def _tree(*dirs):

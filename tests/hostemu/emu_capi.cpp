@@ -27,7 +27,7 @@ namespace
 	{
 		static ref_gblock_fn fn = [] {
 			const char* path = std::getenv("QB_EMU_REF");
-			void* so = dlopen(path ? path : "oracle/_ref/libqboot_ref.so", RTLD_NOW | RTLD_LOCAL);
+			void* so = dlopen(path ? path : "oracle/_ref/libqboot_ref.so", RTLD_NOW | RTLD_LOCAL | RTLD_DEEPBIND);
 			if (!so) return ref_gblock_fn(nullptr);
 			return reinterpret_cast<ref_gblock_fn>(dlsym(so, "ref_gblock"));
 		}();

@@ -1,5 +1,5 @@
-"""N > 1 path on CPU (gloo, world_size 2): the shard plan of the benchmark / scan driver and the timing reduction.
-Tables are independent, so ranks own disjoint slices of the key list and exchange nothing on the data path."""
+"""N > 1 path on CPU (gloo, world_size 2): the shard plan of the benchmark / scan driver (keys sorted by cost class and
+dealt round-robin), the gather of the ranks' tables to rank 0 and the timing reduction."""
 import os
 import socket
 
@@ -22,12 +22,26 @@ def _worker(rank, world, port, n, q):
     import bench
     from qboot_b200 import workload as wl
 
-    spin, delta, S, P = bench.make_shard(rank, n)
+    spin, delta, S, P = bench.make_shard(rank, world, n * world)
     assert len(spin) == n
-    # every rank can compute every other rank's slice: compare against the unsharded list
+    # every rank can compute every other rank's share: the unsharded list, sorted by cost class, dealt round-robin
     keys = wl.sweep_keys(bench.PREC, bench.LAM, bench.NUMAX, bench.MAXSPIN, n * world)
-    fs, fd, fS, fP = wl.to_records(keys[rank * n:(rank + 1) * n], bench.PREC)
+    order = sorted(range(len(keys)), key=lambda i: (keys[i][0] != 0, i))
+    fs, fd, fS, fP = wl.to_records([keys[i] for i in order[rank::world]], bench.PREC)
     assert np.array_equal(spin, fs) and np.array_equal(delta, fd) and np.array_equal(S, fS) and np.array_equal(P, fP)
+    # cost classes are balanced: the ranks' counts of spin-0 tables differ by at most one
+    z = torch.tensor([int((spin == 0).sum())], dtype=torch.int64)
+    zs = [torch.zeros_like(z) for _ in range(world)]
+    dist.all_gather(zs, z)
+    assert max(int(x) for x in zs) - min(int(x) for x in zs) <= 1
+    # the benchmark's data-path collective: every rank's (stand-in) tables gathered into rank 0's buffer, in rank order
+    mine = torch.from_numpy(delta.view(np.uint8).reshape(-1).copy())
+    got = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, got, dst=0)
+    if rank == 0:
+        for r in range(world):
+            want = wl.to_records([keys[i] for i in order[r::world]], bench.PREC)[1]
+            assert np.array_equal(got[r].numpy().view(np.uint32).reshape(want.shape), want)
     # checksum of checksums: the union of the shards is the unsharded list, no overlap
     h = torch.tensor([int(np.bitwise_xor.reduce(delta.view(np.uint32).ravel().astype(np.uint64) * np.uint64(2654435761) % np.uint64(2**61)))], dtype=torch.int64)
     hs = [torch.zeros_like(h) for _ in range(world)]

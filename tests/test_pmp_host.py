@@ -47,3 +47,36 @@ def test_fractional_dimension(facade_emu, ref, tmp_path):
     ref.build_pmp(600, 40, 7, "37/10", 0, 0, False, ds="0.8", de="2.2", numax=4, maxspin=6, threads=2, outdir=want)
     qb.build_pmp(600, 40, 7, "37/10", 0, 0, False, ds="0.8", de="2.2", numax=4, maxspin=6, threads=2, outdir=got, lib=facade_emu)
     assert same_dirs(got, want) == []
+
+
+REF_SRC = "/root/reference"
+
+
+@pytest.mark.parametrize("src,theirs,args", [
+    ("sample/main.cpp", "sample_ref", ()),            # single-correlator Ising, 1000-bit, n_Max 400, lambda 16, FindContradiction
+    ("test/src/main.cpp", "testmain_ref", ("solve",)),  # mixed Ising, 1000-bit, n_Max 400, lambda 14, ExtremalOPE
+])
+def test_reference_drivers_compile_unmodified_against_the_facade(facade_emu, ref, tmp_path, src, theirs, args):
+    """The reference's own driver programs, UNMODIFIED, compiled against include/qboot and linked with the facade (here over
+    the host stand-in of the C ABI; tests/test_gpu.py runs the copies linked with the CUDA library): same SDPB directory,
+    byte for byte, as the same source linked with the reference."""
+    import subprocess
+
+    from tests.conftest import ROOT
+
+    theirs = os.path.join(ROOT, "oracle", "_ref", theirs)
+    if not (os.path.isdir(REF_SRC) and os.path.exists(theirs)):
+        pytest.skip("needs /root/reference (driver sources) and oracle/_ref")
+    bdir = os.path.join(ROOT, "tests", "_build")
+    exe = str(tmp_path / "driver_emu")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-DNDEBUG", "-w", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(REF_SRC, src), "-o", exe, "-L" + bdir, "-lqboot_facade_emu", "-lqb_emu",
+                           "-Wl,-rpath," + bdir, "-pthread"])
+    dirs = []
+    for prog, cwd in ((exe, tmp_path / "ours"), (theirs, tmp_path / "ref")):
+        os.makedirs(cwd)
+        subprocess.run([prog, *args], cwd=cwd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+        (d,) = os.listdir(cwd)
+        dirs.append((d, str(cwd / d)))
+    assert dirs[0][0] == dirs[1][0]
+    assert same_dirs(dirs[0][1], dirs[1][1]) == []
