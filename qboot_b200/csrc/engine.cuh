@@ -147,16 +147,17 @@ namespace qb
 		uint32_t* t_spin = nullptr;
 		T *j_delta = nullptr, *j_S = nullptr, *j_P = nullptr, *j_b0 = nullptr;
 		uint32_t* j_spin = nullptr;
-		std::vector<cudaEvent_t> ev;    // 5 per chunk when timing
+		std::vector<cudaEvent_t> ev;    // timing: one in front of every stage (tick)
+		std::vector<int> ev_stage;      // stage that follows ev[i], -1 none
+		size_t ev_used = 0;
+		std::vector<int> group_c;       // chunk boundaries of the front groups
 		cudaStream_t lo_stream = nullptr, mid_stream = nullptr, fin_stream = nullptr;  // wide kernels of all chunks, by stage
-		std::vector<cudaStream_t> hi_streams;    // latency-bound kernels, one stream per chunk
-		std::vector<cudaEvent_t> dep_ev;         // 4 per chunk
+		std::vector<cudaEvent_t> dep_ev;         // one per front group + two per chunk
 		cudaEvent_t fork_ev = nullptr, copy_done_ev = nullptr, fin_done_ev = nullptr, lo_done_ev = nullptr;
 		cudaStream_t copy_stream = nullptr;      // device -> host copies of finished chunks (fetch_dst)
-		int hi_priority = 0;
 		std::vector<int> job_of_table;  // first job of every table (+ sentinel)
 		std::vector<int> chunk_t;       // table boundaries of the chunks
-		int n_chunks = 1, timed_chunks = 0, sm_count = 0;
+		int n_chunks = 1, sm_count = 0;
 		size_t a_slot_records = 0;      // records of the scaled-coefficient scratch (largest chunk)
 
 		Engine(int dev, int prec_bits)
@@ -176,7 +177,6 @@ namespace qb
 			for (cudaEvent_t e_ : dep_ev) cudaEventDestroy(e_);
 			for (cudaEvent_t e_ : {fork_ev, copy_done_ev, fin_done_ev, lo_done_ev})
 				if (e_) cudaEventDestroy(e_);
-			for (cudaStream_t s : hi_streams) cudaStreamDestroy(s);
 			for (cudaStream_t s_ : {lo_stream, mid_stream, fin_stream, copy_stream})
 				if (s_) cudaStreamDestroy(s_);
 			if (stream) cudaStreamDestroy(stream);
@@ -418,6 +418,14 @@ namespace qb
 				n_chunks = n > chunk ? int((n + chunk - 1) / chunk) : 1;
 				chunk_t.assign(size_t(n_chunks) + 1, n);
 				for (int c = 0; c < n_chunks; ++c) chunk_t[size_t(c)] = int(std::min<int64_t>(n, chunk * c));
+				// front groups: whole chunks, about two waves of k_series (one thread per job, 4 CTAs of 128 per SM) each
+				static const int env_front = std::getenv("QB_FRONT") ? std::max(256, std::atoi(std::getenv("QB_FRONT"))) : 0;
+				const int64_t front = env_front ? env_front : int64_t(2) * sm_count * 4 * 128;
+				group_c.assign(1, 0);
+				for (int c = 1; c <= n_chunks; ++c)
+					if (c == n_chunks || chunk_t[size_t(c)] - chunk_t[size_t(group_c.back())] >= front) group_c.push_back(c);
+				// a short last group joins its predecessor
+				if (group_c.size() > 2 && n - chunk_t[size_t(group_c[group_c.size() - 2])] < front / 2) group_c.erase(group_c.end() - 2);
 			}
 			int max_chunk = 0;
 			for (int c = 0; c < n_chunks; ++c) max_chunk = std::max(max_chunk, chunk_t[size_t(c) + 1] - chunk_t[size_t(c)]);
@@ -505,52 +513,79 @@ namespace qb
 			                      rec * size_t(r.t1 - r.t0), cudaMemcpyDeviceToHost, st));
 			return 0;
 		}
-		// one chunk, all stages back to back on one stream, optionally with an event around every stage
-		int run_serial(int c, cudaStream_t st, cudaEvent_t* ev)
+		// ---- scheduling ---------------------------------------------------------------------------------------------------
+		// The batch is cut into chunks (table ranges; the scaled-coefficient scratch is one chunk-sized slot) and the chunks
+		// are gathered into FRONT GROUPS of about two waves of the series kernel.  The front stages -- recurrence
+		// coefficients, series recurrence, powers: one thread per job / table, a long dependent chain each -- are launched
+		// once per group so that every scheduler has its four warps; the wide stages run chunk by chunk:
+		//   lo_stream   coefficients + series + powers of every group, in order
+		//   mid_stream  scale + Horner of every chunk, in order (they share the one `a` scratch slot)
+		//   fin_stream  rho -> z + transverse recursion (instruction-fetch-bound, low issue rate); copy_stream the copy-out
+		// so the front stages of group g + 1 run underneath the wide stages of group g and the kernels fill each other's
+		// tails.  Events carry the dependencies; everything forks from and joins the handle's stream.
+		// With timing enabled (or QB_DEBUG_SYNC / QB_SERIAL) everything runs in order on the handle's stream instead, with an
+		// event in front of every stage.
+		Range group_range(int g) const
 		{
-			const Range r = range_of(c);
-			const bool timed = ev != nullptr;
-			if (timed) QB_CU(cudaEventRecord(ev[0], st));
-			stage_rec(r, st);
-			if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
-			if (timed) QB_CU(cudaEventRecord(ev[1], st));
-			stage_series(r, st);
-			if (int rc_ = debug_sync("k_series")) return rc_;
-			if (timed) QB_CU(cudaEventRecord(ev[2], st));
-			stage_pow(r, st);
-			stage_deriv(r, st);
-			if (int rc_ = debug_sync("k_pow/k_scale/k_horner")) return rc_;
-			if (timed) QB_CU(cudaEventRecord(ev[3], st));
-			stage_finish(r, st);
-			if (int rc_ = debug_sync("k_finish")) return rc_;
-			if (timed) QB_CU(cudaEventRecord(ev[4], st));
-			if (fetch_dst)
-				if (int rc_ = copy_chunk_out(r, st)) return rc_;
+			const int t0 = chunk_t[size_t(group_c[size_t(g)])], t1 = chunk_t[size_t(group_c[size_t(g) + 1])];
+			return Range{t0, t1, job_of_table[size_t(t0)], job_of_table[size_t(t1)]};
+		}
+		// timing: an event in front of stage `stage` (0 coefficients, 1 series, 2 powers + derivatives, 3 finish, -1 end)
+		int tick(int stage, cudaStream_t st)
+		{
+			if (!timing) return 0;
+			if (ev_used == ev.size())
+			{
+				cudaEvent_t x;
+				QB_CU(cudaEventCreate(&x));
+				ev.push_back(x);
+			}
+			QB_CU(cudaEventRecord(ev[ev_used++], st));
+			ev_stage.push_back(stage);
 			return 0;
 		}
-		// The batch is cut into chunks.  The wide, throughput-bound kernels (coefficients, polynomial values, scale, Horner)
-		// of all chunks are serialised on one low-priority stream; the one-thread-per-table, latency-bound kernels (powers,
-		// series recurrence, transverse recursion) of every chunk run on that chunk's own high-priority stream, so that
-		// they overlap each other and the wide kernels of the neighbouring chunks.  Events carry the dependencies.
-		// With timing enabled (or QB_DEBUG_SYNC) everything runs chunk after chunk on the handle's stream instead.
+		int run_serial(cudaStream_t st)
+		{
+			ev_used = 0;
+			ev_stage.clear();
+			const int n_groups = int(group_c.size()) - 1;
+			for (int g = 0; g < n_groups; ++g)
+			{
+				const Range R = group_range(g);
+				if (int rc_ = tick(0, st)) return rc_;
+				stage_rec(R, st);
+				if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
+				if (int rc_ = tick(1, st)) return rc_;
+				stage_series(R, st);
+				if (int rc_ = debug_sync("k_series")) return rc_;
+				if (int rc_ = tick(2, st)) return rc_;
+				stage_pow(R, st);
+				if (int rc_ = debug_sync("k_pow")) return rc_;
+				for (int c = group_c[size_t(g)]; c < group_c[size_t(g) + 1]; ++c)
+				{
+					const Range r = range_of(c);
+					if (int rc_ = tick(2, st)) return rc_;
+					stage_deriv(r, st);
+					if (int rc_ = debug_sync("k_scale/k_horner")) return rc_;
+					if (int rc_ = tick(3, st)) return rc_;
+					stage_finish(r, st);
+					if (int rc_ = debug_sync("k_finish")) return rc_;
+					if (int rc_ = tick(-1, st)) return rc_;
+					if (fetch_dst)
+						if (int rc_ = copy_chunk_out(r, st)) return rc_;
+				}
+			}
+			return tick(-1, st);
+		}
 		int gblock_run() override
 		{
 			if (!has_ctx) return -3;
 			if (n_tables == 0) return 0;
 			QB_CU(cudaSetDevice(device));
-			if (timing)
-				while (ev.size() < size_t(5) * size_t(n_chunks))
-				{
-					cudaEvent_t x;
-					QB_CU(cudaEventCreate(&x));
-					ev.push_back(x);
-				}
 			static const bool serial_env = std::getenv("QB_DEBUG_SYNC") != nullptr || std::getenv("QB_SERIAL") != nullptr;
 			if (timing || n_chunks == 1 || serial_env)
 			{
-				timed_chunks = timing ? n_chunks : 0;
-				for (int c = 0; c < n_chunks; ++c)
-					if (int rc = run_serial(c, stream, timing ? ev.data() + 5 * c : nullptr)) return rc;
+				if (int rc = run_serial(stream)) return rc;
 				QB_CU(cudaGetLastError());
 				tables_valid = true;
 				return 0;
@@ -567,56 +602,45 @@ namespace qb
 				QB_CU(cudaEventCreateWithFlags(&fin_done_ev, cudaEventDisableTiming));
 				QB_CU(cudaEventCreateWithFlags(&lo_done_ev, cudaEventDisableTiming));
 				QB_CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-				hi_priority = pr_hi;
 			}
-			while (int(hi_streams.size()) < n_chunks)
+			const int n_groups = int(group_c.size()) - 1;
+			while (dep_ev.size() < size_t(n_groups) + 2 * size_t(n_chunks))
 			{
-				cudaStream_t s;
-				QB_CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi_priority));
-				hi_streams.push_back(s);
-				for (int i = 0; i < 4; ++i)
-				{
-					cudaEvent_t x;
-					QB_CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
-					dep_ev.push_back(x);
-				}
+				cudaEvent_t x;
+				QB_CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+				dep_ev.push_back(x);
 			}
-			auto EV = [&](int c, int i) { return dep_ev[size_t(4 * c + i)]; };  // 0 poly done, 1 series done, 2 horner done, 3 finish done
-			// Three low-priority streams for the wide stages, so that their kernels fill each other's tails and stalls:
-			//   lo_stream   coefficients + polynomial values of every chunk, in order
-			//   mid_stream  scale + Horner of every chunk, in order (they share the one `a` scratch slot)
-			//   fin_stream  rho -> z + transverse recursion (instruction-fetch-bound, low issue rate) and the copy-out
-			// plus one high-priority stream per chunk for the latency-bound powers and series recurrence.
+			auto GE = [&](int g) { return dep_ev[size_t(g)]; };                               // front stages of group g done
+			auto EV = [&](int c, int i) { return dep_ev[size_t(n_groups) + size_t(2 * c + i)]; };  // 0 horner done, 1 finish done
 			QB_CU(cudaEventRecord(fork_ev, stream));
 			for (cudaStream_t s_ : {lo_stream, mid_stream, fin_stream}) QB_CU(cudaStreamWaitEvent(s_, fork_ev, 0));
-			for (int c = 0; c < n_chunks; ++c) QB_CU(cudaStreamWaitEvent(hi_streams[size_t(c)], fork_ev, 0));
-			for (int c = 0; c < n_chunks; ++c)
+			for (int g = 0; g < n_groups; ++g)
 			{
-				const Range r = range_of(c);
-				stage_rec(r, lo_stream);
-				QB_CU(cudaEventRecord(EV(c, 0), lo_stream));
-				cudaStream_t hs = hi_streams[size_t(c)];
-				stage_pow(r, hs);
-				QB_CU(cudaStreamWaitEvent(hs, EV(c, 0), 0));
-				stage_series(r, hs);
-				QB_CU(cudaEventRecord(EV(c, 1), hs));
+				const Range R = group_range(g);
+				stage_rec(R, lo_stream);
+				stage_series(R, lo_stream);
+				stage_pow(R, lo_stream);
+				QB_CU(cudaEventRecord(GE(g), lo_stream));
 			}
-			for (int c = 0; c < n_chunks; ++c)
+			for (int g = 0; g < n_groups; ++g)
 			{
-				const Range r = range_of(c);
-				QB_CU(cudaStreamWaitEvent(mid_stream, EV(c, 1), 0));
-				stage_deriv(r, mid_stream);
-				QB_CU(cudaEventRecord(EV(c, 2), mid_stream));
-				QB_CU(cudaStreamWaitEvent(fin_stream, EV(c, 2), 0));
-				stage_finish(r, fin_stream);
-				if (fetch_dst)
+				QB_CU(cudaStreamWaitEvent(mid_stream, GE(g), 0));
+				for (int c = group_c[size_t(g)]; c < group_c[size_t(g) + 1]; ++c)
 				{
-					QB_CU(cudaEventRecord(EV(c, 3), fin_stream));
-					QB_CU(cudaStreamWaitEvent(copy_stream, EV(c, 3), 0));
-					if (int rc_ = copy_chunk_out(r, copy_stream)) return rc_;
+					const Range r = range_of(c);
+					stage_deriv(r, mid_stream);
+					QB_CU(cudaEventRecord(EV(c, 0), mid_stream));
+					QB_CU(cudaStreamWaitEvent(fin_stream, EV(c, 0), 0));
+					stage_finish(r, fin_stream);
+					if (fetch_dst)
+					{
+						QB_CU(cudaEventRecord(EV(c, 1), fin_stream));
+						QB_CU(cudaStreamWaitEvent(copy_stream, EV(c, 1), 0));
+						if (int rc_ = copy_chunk_out(r, copy_stream)) return rc_;
+					}
 				}
 			}
-			// join: fin_stream is behind mid_stream, which is behind every series stream; lo_stream is behind nothing
+			// join: fin_stream is behind mid_stream, which is behind lo_stream
 			QB_CU(cudaEventRecord(fin_done_ev, fin_stream));
 			QB_CU(cudaStreamWaitEvent(stream, fin_done_ev, 0));
 			QB_CU(cudaEventRecord(lo_done_ev, lo_stream));
@@ -630,22 +654,22 @@ namespace qb
 			tables_valid = true;
 			return 0;
 		}
-		// after a synchronise: read the per-kernel times of the last run
+		// after a synchronise: read the per-stage times of the last run
 		int collect_times()
 		{
 			for (float& x : kernel_ms) x = 0.f;
 			if (!timing) return 0;
-			for (int c = 0; c < timed_chunks; ++c)
-				for (int i = 0; i < 4; ++i)
+			for (size_t i = 0; i + 1 < ev_used && i + 1 < ev_stage.size(); ++i)
+			{
+				if (ev_stage[i] < 0) continue;
+				float ms = 0.f;
+				if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess)
 				{
-					float ms = 0.f;
-					if (cudaEventElapsedTime(&ms, ev[size_t(5 * c + i)], ev[size_t(5 * c + i + 1)]) != cudaSuccess)
-					{
-						cudaGetLastError();
-						ms = 0.f;
-					}
-					kernel_ms[i] += ms;
+					cudaGetLastError();
+					ms = 0.f;
 				}
+				kernel_ms[ev_stage[i]] += ms;
+			}
 			return 0;
 		}
 		int collect_times_public() override { return collect_times(); }

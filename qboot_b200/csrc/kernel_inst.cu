@@ -45,7 +45,7 @@ namespace qb
 			return true;
 		}();
 		(void)attr_set;
-		k_series<QB_L><<<(n_jobs + 31) / 32, QB_SERIES_THREADS, series_smem_bytes<QB_L>(), st>>>(cx, n_jobs, delta, spin, b0, coef, b);
+		k_series<QB_L><<<(n_jobs + QB_SERIES_THREADS - 1) / QB_SERIES_THREADS, QB_SERIES_THREADS, series_smem_bytes<QB_L>(), st>>>(cx, n_jobs, delta, spin, b0, coef, b);
 	}
 #elif QB_KGROUP == 2
 	template <>

@@ -2,7 +2,7 @@
 // group so that each translation unit (kernel_inst.cu -DQB_KGROUP=g) only parses what it instantiates:
 //   kernels_g0.cuh  k_rec_coeffs  one thread per (series job, recurrence coefficient)              -> coef[job][40]
 //                   k_ops         diagnostic: one primitive elementwise
-//   kernels_g1.cuh  k_series      32 series jobs per CTA: a producer warp (recurrence polynomials at n+1) feeding a consumer warp (the chain) -> b[job][0..n_max]
+//   kernels_g1.cuh  k_series      one thread per series job over the whole batch: recurrence polynomials + the chain  -> b[job][0..n_max]
 //   kernels_g2.cuh  k_scale       one thread per (table, n): the lambda+1 scaled coefficient arrays -> a[table][k][n]
 //                   k_horner      one thread per (table, k): Horner sum, times rho^q / k!           -> fr[table][k]
 //   kernels_g3.cuh  k_rho_to_z, k_offdiag_val, k_offdiag_close: rho->z matrix and the transverse recursion, level by level -> g[table][dim_M]
@@ -19,23 +19,6 @@
 
 namespace qb
 {
-	// record <-> shared memory, word-major with the 32 lanes of a warp side by side (conflict free): word w of lane l at base[w * 32 + l]
-	template <int L>
-	__device__ __forceinline__ void sts_rec(uint32_t* base, const mpf<L>& s)
-	{
-		base[0] = s.sk;
-		base[32] = uint32_t(s.exp);
-#pragma unroll
-		for (int j = 0; j < L; ++j) base[(2 + j) * 32] = s.m[j];
-	}
-	template <int L>
-	__device__ __forceinline__ void lds_rec(mpf<L>& d, const uint32_t* base)
-	{
-		d.sk = base[0];
-		d.exp = int32_t(base[32]);
-#pragma unroll
-		for (int j = 0; j < L; ++j) d.m[j] = base[(2 + j) * 32];
-	}
 	template <int L>
 	__device__ __forceinline__ void ldg_rec64(mpf<L>& d, const mpf<L>* src)
 	{
@@ -57,44 +40,61 @@ namespace qb
 			copy(d, *src);
 	}
 
-	// The series recurrence b[n] = -(sum_{i=1}^{min(n,K-1)} p_i(n) b[n-i]) / p_0(n)       (src/hor_recursion.cpp:31-37)
-	// for 32 jobs per CTA, as a two-warp producer / consumer pair:
-	//   warp 1 (producer) evaluates the K recurrence polynomials at n + 1 by Horner with the integer n, exactly as the
-	//          reference's Polynomial::eval does (include/qboot/algebra/polynomial.hpp:66-83: mul_ui, add, each rounded),
-	//          into one half of a double buffer in shared memory;
-	//   warp 0 (consumer) runs the dependent chain of step n -- K - 1 fused multiply-adds and one division -- reading
-	//          the p_i(n) of the other half.
-	// The polynomial values are independent of the series, so the producer is never on the critical path, and they never
-	// travel through HBM (a separate k_polyvals kernel used to write 435 KB per table and cost 12 % of the kernel time).
-	constexpr int QB_SERIES_THREADS = 64;
+	// The series recurrence b[n] = -(sum_{i=1}^{min(n,K-1)} p_i(n) b[n-i]) / p_0(n)       (src/hor_recursion.cpp:31-37),
+	// one thread per series job, launched over ALL jobs of a batch at once: the recurrence is a chain of n_max dependent
+	// steps, so the only parallelism is across jobs, and the limb-product pipe needs >= 4 resident warps per scheduler to
+	// stay busy (a chunk-sized launch left most schedulers with no warp at all: 8 % of the limb-product peak).
+	//   * the recurrence polynomials p_i(n) are evaluated in the thread, right before they are used, by Horner with the
+	//     integer n exactly as the reference's Polynomial::eval does (include/qboot/algebra/polynomial.hpp:66-83: mul_ui,
+	//     add, each rounded): they never travel through HBM (a separate k_polyvals kernel used to write 435 KB per table);
+	//   * p_i(n) -- the row operand of the product -- and the running sum live in SHARED memory, limb-major and
+	//     conflict-free (limb j of thread x at sh[j * 128 + x]), like the chain operands of k_scale / k_horner: the rolled
+	//     product loop indexes its row operand dynamically, and thread-local records of 75 k resident threads overflow L1;
+	//   * one copy of the product code serves the first term (a plain rounded product) and the fused multiply-adds.
+	constexpr int QB_SERIES_THREADS = 256;
 	template <int L>
 	constexpr size_t series_smem_bytes()
 	{
-		return size_t(2) * 8 * (L + 2) * 32 * sizeof(uint32_t);
+		return size_t(2) * L * QB_SERIES_THREADS * sizeof(uint32_t);
 	}
 	template <int L>
-	__global__ void __launch_bounds__(QB_SERIES_THREADS)
+	__device__ __forceinline__ void series_store(uint32_t* my, uint32_t& sk, int32_t& exp, const mpf<L>& v)
+	{
+		sk = v.sk;
+		exp = v.exp;
+#pragma unroll
+		for (int j = 0; j < L; ++j) my[j * QB_SERIES_THREADS] = v.m[j];
+	}
+	template <int L>
+	__device__ __forceinline__ void series_load(mpf<L>& v, const uint32_t* my, uint32_t sk, int32_t exp)
+	{
+		v.sk = sk;
+		v.exp = exp;
+#pragma unroll
+		for (int j = 0; j < L; ++j) v.m[j] = my[j * QB_SERIES_THREADS];
+	}
+	template <int L>
+	__global__ void __launch_bounds__(QB_SERIES_THREADS, 512 / QB_SERIES_THREADS)
 	    k_series(DevCtx cx, int n_jobs, const mpf<L>* __restrict__ delta, const uint32_t* __restrict__ spin, const mpf<L>* __restrict__ b0,
 	             const mpf<L>* __restrict__ coef, mpf<L>* __restrict__ b)
 	{
-		extern __shared__ uint32_t pvbuf[];
-		constexpr int W = L + 2;
-		const int lane = threadIdx.x & 31;
-		const bool producer = (threadIdx.x >> 5) != 0;
-		const int job = blockIdx.x * 32 + lane;
+		extern __shared__ uint32_t sh[];
+		uint32_t* myp = sh + threadIdx.x;                           // p_i(n)
+		uint32_t* mys = sh + L * QB_SERIES_THREADS + threadIdx.x;   // running sum
+		const int job = blockIdx.x * QB_SERIES_THREADS + threadIdx.x;
 		const int prec = cx.prec;
 		const uint32_t n_max = cx.n_max;
 		bool active = job < n_jobs;
 		mpf<L>* bj = b + size_t(active ? job : 0) * (n_max + 1);
-		if (active && is_zero(delta[job]))
+		if (active)
 		{
-			// unit operator: b = (b0, 0, 0, ...)                                  (src/hor_recursion.cpp:20)
-			if (!producer)
+			copy(bj[0], b0[job]);
+			if (is_zero(delta[job]))
 			{
-				copy(bj[0], b0[job]);
+				// unit operator: b = (b0, 0, 0, ...)                                  (src/hor_recursion.cpp:20)
 				for (uint32_t n = 1; n <= n_max; ++n) set_zero(bj[n]);
+				active = false;
 			}
-			active = false;
 		}
 		int K = 8, deg = 4;
 		if (active && spin[job] == 0)
@@ -106,60 +106,78 @@ namespace qb
 		asm volatile("" : "+r"(K), "+r"(deg));
 		const int st = deg + 1;
 		const mpf<L>* c = coef + size_t(active ? job : 0) * QB_NCOEF;
-		auto slot = [&](uint32_t n, int i) { return pvbuf + ((size_t(n & 1u) * 8 + size_t(i)) * W) * 32 + lane; };
-		auto produce = [&](uint32_t n) {
-			QB_ROLL
-			for (int i = 0; i < K; ++i)
-			{
-				mpf<L> s, cd;
-				ldg_rec64(s, &c[i * st + deg]);
-				QB_ROLL
-				for (int d = deg - 1; d >= 0; --d)
-				{
-					fast::mul_small(s, s, int64_t(n), prec);
-					ldg_rec64(cd, &c[i * st + d]);
-					fast::add(s, s, cd, prec);
-				}
-				sts_rec(slot(n, i), s);
-			}
-		};
-		if (active)
-		{
-			if (producer)
-				produce(1u);
-			else
-				copy(bj[0], b0[job]);
-		}
-		__syncthreads();
+		uint32_t psk, ssk = K_ZERO;
+		int32_t pexp, sexp = 0;
 		for (uint32_t n = 1; n <= n_max; ++n)
 		{
-			if (active)
+			// i = 1 .. 7: the terms of the sum (those with i < K, i <= n); i = 8: the divisor p_0(n).
+			// The warps of the CTA walk the body together (a barrier per term): one pass over the ~5 k instructions of a term
+			// costs an instruction fetch per SM instead of one per warp -- unsynchronised, this kernel spent 9 of 10 issue
+			// slots waiting for instructions.
+			QB_ROLL
+			for (int i = 1; i <= 8; ++i)
 			{
-				if (producer)
+				__syncthreads();
+				const bool divisor = i == 8;
+				if (!active || (!divisor && (i >= K || uint32_t(i) > n))) continue;
+				const int ip = divisor ? 0 : i;
+				mpf<L> p;
 				{
-					if (n < n_max) produce(n + 1u);
-				}
-				else
-				{
-					mpf<L> sum, bn, p, bp;
-					lds_rec(p, slot(n, 1));
-					ldg_rec64(bp, &bj[n - 1]);
-					fast::mul(sum, p, bp, prec);  // fma(0, p_1 b[n-1]) rounds like the product
+					mpf<L> cd;
+					ldg_rec64(p, &c[ip * st + deg]);
 					QB_ROLL
-					for (int i = 2; i < K; ++i)
-						if (uint32_t(i) <= n)
-						{
-							lds_rec(p, slot(n, i));
-							ldg_rec64(bp, &bj[n - uint32_t(i)]);
-							fast::fma(sum, p, bp, sum, prec);
-						}
+					for (int d = deg - 1; d >= 0; --d)
+					{
+						fast::mul_small(p, p, int64_t(n), prec);
+						ldg_rec64(cd, &c[ip * st + d]);
+						fast::add(p, p, cd, prec);
+					}
+				}
+				if (divisor)
+				{
+					// b[n] = -sum / p_0(n)
+					mpf<L> sum, bn;
+					series_load(sum, mys, ssk, sexp);
 					neg(sum);
-					lds_rec(p, slot(n, 0));
 					fast::div(bn, sum, p, prec);
 					copy(bj[n], bn);
+					continue;
+				}
+				mpf<L> bp;
+				ldg_rec64(bp, &bj[n - uint32_t(i)]);
+				bool done = false;
+				if ((p.sk & 3u) == K_REG && (bp.sk & 3u) == K_REG && (i == 1 || (ssk & 3u) == K_REG))
+				{
+					series_store(myp, psk, pexp, p);
+					uint32_t X[L + 3], stt;
+					int32_t e;
+					fast::product_frame<L, QB_SERIES_THREADS>(X, stt, e, myp, pexp, bp);
+					const uint32_t sgn = (psk ^ bp.sk) & SIGN_BIT;
+					mpf<L> r;
+					if (i == 1)
+						done = fast::round_frame<L>(r, sgn, e, X + 1, stt, prec);  // fma(+0, p_1 b[n-1]) rounds like the product
+					else
+					{
+						mpf<L> sum;
+						series_load(sum, mys, ssk, sexp);
+						done = fast::addround<L>(r, sgn, e, X + 1, stt, sum, prec);
+					}
+					if (done) series_store(mys, ssk, sexp, r);
+				}
+				if (!done)
+				{
+					// special values, deep cancellation: the generic routines (same correctly rounded result)
+					mpf<L> sum, r;
+					if (i == 1)
+						mul(r, p, bp, prec);
+					else
+					{
+						series_load(sum, mys, ssk, sexp);
+						fma(r, p, bp, sum, prec);
+					}
+					series_store(mys, ssk, sexp, r);
 				}
 			}
-			__syncthreads();
 		}
 	}
 
