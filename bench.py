@@ -266,19 +266,45 @@ def main():
     eng.plan(spin, delta, S, P)
     peak = eng.imad_peak(4096)
     eng.set_timing(False)
-    gathered = None
-    if world > 1:
-        # rank 0 receives every rank's tables (its own included) into one buffer in its HBM
-        mine = torch.as_tensor(_DevBytes(eng.lib.qb_gblock_device_tables(eng.h), n * table_bytes), device=f"cuda:{local}")
-        gathered = [torch.empty(n * table_bytes, dtype=torch.uint8, device=f"cuda:{local}") for _ in range(world)] if rank == 0 else None
+    # ---- the gather (N > 1): every rank's tables end up in ONE buffer in rank 0's HBM.  Rank 0 allocates it and exports a
+    # CUDA IPC handle; every rank opens it and names its slice as the sink of its runs: each finished chunk is then copied
+    # there by the copy engine over NVLink underneath the kernels of the later chunks (no collective on the data path;
+    # torch.distributed only carries the 64-byte handle, the barriers and the timing reduction).  QB_GATHER=nccl selects the
+    # plain alternative, torch.distributed.gather after the last kernel.
+    gather_mode = os.environ.get("QB_GATHER", "peer") if world > 1 else "none"
+    shard_bytes = n * table_bytes
+    gathered, mine, sink_base, sink_local = None, None, None, None
+    if world > 1 and gather_mode == "peer":
+        import ctypes as C
+
+        handle = torch.zeros(64, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            sink_base = eng.lib.qb_device_alloc(eng.h, world * shard_bytes)
+            if not sink_base:
+                raise SystemExit("qb_device_alloc failed")
+            hb = (C.c_ubyte * 64)()
+            eng._check(eng.lib.qb_ipc_export(eng.h, sink_base, hb), "qb_ipc_export")
+            handle.copy_(torch.tensor(list(hb), dtype=torch.uint8))
+        dist.broadcast(handle, src=0)
+        if rank != 0:
+            hb = (C.c_ubyte * 64)(*handle.cpu().tolist())
+            ptr = C.c_void_p()
+            eng._check(eng.lib.qb_ipc_open(eng.h, hb, C.byref(ptr)), "qb_ipc_open")
+            sink_base = ptr.value
+        sink_local = sink_base + rank * shard_bytes
+        eng._check(eng.lib.qb_gblock_set_sink(eng.h, sink_local), "qb_gblock_set_sink")
+    elif world > 1:
+        mine = torch.as_tensor(_DevBytes(eng.lib.qb_gblock_device_tables(eng.h), shard_bytes), device=f"cuda:{local}")
+        gathered = [torch.empty(shard_bytes, dtype=torch.uint8, device=f"cuda:{local}") for _ in range(world)] if rank == 0 else None
 
     gev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (args.steps + args.warmup))]
 
     def step(i):
-        # all kernels over the resident shard (chunks spread over the engine's streams, joined on the handle's stream), then
-        # the gather on the same stream: NCCL waits for the tables and the stream waits for NCCL, no host synchronisation
+        # all kernels over the resident shard (front groups and chunks spread over the engine's streams, joined on the
+        # handle's stream) -- with the peer sink the copies to rank 0 ride along; with QB_GATHER=nccl the collective follows
+        # on the same stream (NCCL waits for the tables and the stream waits for NCCL, no host synchronisation)
         eng.run()
-        if world > 1:
+        if mine is not None:
             with torch.cuda.stream(stream):
                 gev[2 * i].record(stream)
                 dist.gather(mine, gathered, dst=0)
@@ -306,9 +332,33 @@ def main():
     launches_timed = eng.launches - launches_before
     dev_ms = ev0.elapsed_time(ev1)
     gather_ms = 0.0
-    if world > 1:
+    if mine is not None:
         gather_ms = sum(gev[2 * (args.warmup + i)].elapsed_time(gev[2 * (args.warmup + i) + 1]) for i in range(args.steps)) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    gather_ok, nogather_ms = None, 0.0
+    if world > 1 and gather_mode == "peer":
+        # (not timed) what rank 0 holds is what the ranks computed: a checksum of every rank's tables against the same
+        # checksum of its slice of rank 0's buffer
+        local_t = torch.as_tensor(_DevBytes(eng.lib.qb_gblock_device_tables(eng.h), shard_bytes), device=f"cuda:{local}")
+        cs = local_t.view(torch.int32).to(torch.int64).sum().reshape(1)
+        css = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(css, cs)
+        if rank == 0:
+            allt = torch.as_tensor(_DevBytes(sink_base, world * shard_bytes), device=f"cuda:{local}").view(world, -1)
+            gather_ok = all(int(allt[r].view(torch.int32).to(torch.int64).sum()) == int(css[r]) for r in range(world))
+        # and what the gather costs on top of the kernels: the same steps without the sink
+        eng._check(eng.lib.qb_gblock_set_sink(eng.h, None), "qb_gblock_set_sink")
+        eng.run()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+        for _ in range(args.steps):
+            eng.run()
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        barrier()
+        nogather_ms = e0.elapsed_time(e1) / args.steps
 
     # per-kernel device times (CUDA events on the launching stream around every stage; chunks run back to back on one
     # stream in this mode so that the events bracket exactly one stage each)
@@ -343,13 +393,20 @@ def main():
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------------------
-    stats = torch.tensor([dev_ms, e2e_s, gather_ms, float(n)], dtype=torch.float64, device=f"cuda:{local}")
+    if sink_base:
+        # every rank has stopped writing (barriers above): unmap, then rank 0 frees
+        if rank != 0:
+            eng.lib.qb_ipc_close(eng.h, sink_base)
+        dist.barrier()
+        if rank == 0:
+            eng.lib.qb_device_free(eng.h, sink_base)
+    stats = torch.tensor([dev_ms, e2e_s, gather_ms, float(n), nogather_ms], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s, gather_ms, total_tables = float(mx[0]), float(mx[1]), float(mx[2]), float(sm[3])
+        dev_ms, e2e_s, gather_ms, total_tables, nogather_ms = float(mx[0]), float(mx[1]), float(mx[2]), float(sm[3]), float(mx[4])
     else:
         total_tables = float(n)
     if rank != 0:
@@ -389,9 +446,15 @@ def main():
     }
     if world > 1:
         nv = int((world - 1) * n * table_bytes)
-        line["gather"] = {"ms_per_step": gather_ms, "nvlink_bytes_per_step": nv, "to": "rank 0 HBM",
-                          "how": "torch.distributed.gather over NCCL (grouped send/recv), enqueued behind the tables on the engine's stream",
-                          "gbytes_per_s": (nv / 1e9) / (gather_ms * 1e-3) if gather_ms > 0 else None}
+        if gather_mode == "peer":
+            line["gather"] = {"mode": "peer", "nvlink_bytes_per_step": nv, "to": "rank 0 HBM", "verified": gather_ok,
+                              "how": "every finished chunk is copied by the copy engine into the rank's slice of rank 0's buffer (CUDA IPC, "
+                                     "peer access over NVLink) underneath the kernels of the later chunks; the step ends when the copies have landed",
+                              "ms_per_step_without_gather": nogather_ms, "exposed_ms_per_step": ms_per_step - nogather_ms}
+        else:
+            line["gather"] = {"mode": "nccl", "ms_per_step": gather_ms, "nvlink_bytes_per_step": nv, "to": "rank 0 HBM",
+                              "how": "torch.distributed.gather over NCCL (grouped send/recv), enqueued behind the tables on the engine's stream",
+                              "gbytes_per_s": (nv / 1e9) / (gather_ms * 1e-3) if gather_ms > 0 else None}
     if world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import ref

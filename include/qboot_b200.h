@@ -40,7 +40,8 @@ typedef enum
 	QB_ERR_BAD_ARG = -4,
 	QB_ERR_CUDA = -5,          /* a CUDA call or kernel failed; see qb_last_cuda_error */
 	QB_ERR_RANGE = -6,         /* rational / spin out of the supported range */
-	QB_ERR_NO_MEMORY = -7
+	QB_ERR_NO_MEMORY = -7,
+	QB_ERR_ROUNDING = -8       /* a power stayed next to a rounding boundary at the second Ziv level (probability ~2^-140) */
 } qb_status;
 
 /* Version string of the library. */
@@ -120,6 +121,30 @@ void qb_pinned_free(void* p);
 int qb_set_timing(qb_handle* h, int on);
 int qb_kernel_times(qb_handle* h, float* ms4);
 int qb_imad_peak(qb_handle* h, int iters, double* macs_per_s);
+
+/* ---- Multi-GPU: one process per GPU, one handle each; the key list of a job is dealt to the ranks and every rank's tables
+ * are gathered in ONE rank's HBM ("one exchange, to rank 0", where the PMP is assembled and written).
+ * The exchange is a peer copy over NVLink, not a collective: the root exports its buffer (qb_ipc_export, a 64-byte CUDA IPC
+ * handle that travels by any channel -- the benchmark uses torch.distributed), every rank opens it (qb_ipc_open) and names
+ * its slice as the sink of its runs; from then on every finished chunk of qb_gblock_run is copied to sink + chunk offset
+ * by the copy engine, underneath the kernels of the later chunks, and the handle's stream joins the copies.
+ * The sink may equally be pinned host memory or local device memory; NULL switches it off. */
+int qb_gblock_set_sink(qb_handle* h, void* dst);
+void* qb_device_alloc(qb_handle* h, size_t bytes);   /* cudaMalloc on the handle's device (IPC-exportable); NULL on failure */
+void qb_device_free(qb_handle* h, void* p);
+int qb_ipc_export(qb_handle* h, const void* dev_ptr, unsigned char* handle64);
+int qb_ipc_open(qb_handle* h, const unsigned char* handle64, void** dev_ptr);
+int qb_ipc_close(qb_handle* h, void* dev_ptr);
+
+/* Correct rounding of the powers (mpfr_pow / mpfr_ui_pow at src/hor_recursion.cpp:43, real_function.hpp:262, src/context.cpp:31).
+ * x^y is evaluated as exp(y ln x) with 96 guard bits; when the discarded bits leave the rounding in doubt (they read
+ * 1000...0x or 0111...1x down to bit `bits` of the extended result) the value is recomputed with 192 guard bits (Ziv's
+ * strategy).  qb_set_ziv_slack widens or narrows the in-doubt window -- a test knob: with a wide window a large share of
+ * all powers goes through the second level; 0 restores the default (56, above the 2^46 error bound of the first level).
+ * qb_ziv_counters: out2[0] = powers recomputed at the second level, out2[1] = powers still in doubt there since the handle
+ * was created; a new count in out2[1] makes the next qb_gblock_fetch / qb_gblock_batch return QB_ERR_ROUNDING. */
+int qb_set_ziv_slack(qb_handle* h, int bits);
+int qb_ziv_counters(qb_handle* h, uint64_t* out2);
 
 /* Diagnostic: one arithmetic primitive applied elementwise on the device (n records per operand, HOST memory; unused
  * operands may be NULL).  op: 0 add, 1 sub, 2 mul, 3 div, 4 fma(a*b+c), 6 mul_si(a*ia), 7 add_si, 8 div_si, 9 mul_q

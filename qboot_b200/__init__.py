@@ -23,6 +23,8 @@ SYMBOLS = (
     "qb_vtod_batch", "qb_fblock_tables", "qb_pinned_alloc", "qb_pinned_free",
     "qb_pmp_assemble", "qb_pmp_block_add", "qb_pmp_block_fetch", "qb_pmp_pack", "qb_pmp_packed_fetch", "qb_pmp_text",
     "qb_pmp_text_declined", "qb_pmp_text_patch", "qb_pmp_text_fetch", "qb_pmp_info", "qb_dec_format",
+    "qb_set_ziv_slack", "qb_ziv_counters",
+    "qb_gblock_set_sink", "qb_device_alloc", "qb_device_free", "qb_ipc_export", "qb_ipc_open", "qb_ipc_close",
 )
 # the C++ facade (namespace qboot, include/qboot/*.hpp) built next to the C-ABI library; Python reaches it through the
 # model-level C entry points of qboot_b200/host/models_capi.cpp
@@ -92,6 +94,16 @@ def load_library():
     lib.qb_pmp_text_fetch.argtypes = [C.c_void_p, C.c_void_p]
     lib.qb_pmp_info.argtypes = [C.c_void_p, C.c_void_p]
     lib.qb_dec_format.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.qb_gblock_set_sink.argtypes = [C.c_void_p, C.c_void_p]
+    lib.qb_device_alloc.argtypes = [C.c_void_p, C.c_size_t]
+    lib.qb_device_alloc.restype = C.c_void_p
+    lib.qb_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.qb_device_free.restype = None
+    lib.qb_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.qb_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.qb_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+    lib.qb_set_ziv_slack.argtypes = [C.c_void_p, C.c_int]
+    lib.qb_ziv_counters.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -321,6 +333,17 @@ class Engine:
         v = C.c_double()
         self._check(self.lib.qb_imad_peak(self.h, iters, C.byref(v)), "qb_imad_peak")
         return float(v.value)
+
+    def set_ziv_slack(self, bits: int = 0):
+        """width of the powers' in-doubt window in bits of the extended result's last place (0: default); test knob"""
+        self._check(self.lib.qb_set_ziv_slack(self.h, bits), "qb_set_ziv_slack")
+        return self
+
+    def ziv_counters(self):
+        """(powers recomputed at the second Ziv level, powers still in doubt there) since the handle was created"""
+        out = (C.c_uint64 * 2)()
+        self._check(self.lib.qb_ziv_counters(self.h, out), "qb_ziv_counters")
+        return int(out[0]), int(out[1])
 
     @property
     def launches(self) -> int:

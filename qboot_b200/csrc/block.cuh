@@ -114,9 +114,12 @@ namespace qb
 	// integer) and ONE instance of every primitive -- instead of straight-line code: with all arithmetic force-inlined
 	// the straight-line version was 63 000 instructions (1 MB) per kernel and ran at the speed of instruction fetch
 	// (ncu: 5-10 no-instruction stall cycles per issue).  Operation order and operands are exactly the reference's.
-	template <int L>
+	// LOCKSTEP (device): the CTA meets at a barrier in front of every step, so that its warps run the same primitive at
+	// the same time and one instruction fetch serves all of them (threads without work pass active = false and only
+	// keep the barriers company).
+	template <int L, bool LOCKSTEP = false>
 	QB_HD QB_NOINLINE void offdiag_val(mpf<L>& val, const mpf<L>* f, int64_t fs, int lambda, int m, int n, const mpf<L>& S,
-	                                   const mpf<L>& P, const mpf<L>& qc4, Rational eps, int prec)
+	                                   const mpf<L>& P, const mpf<L>& qc4, Rational eps, int prec, bool active = true)
 	{
 		enum : int { VAL = 0, TERM = 1, T2 = 2, H = 3, RS = 4, RP = 5, RQ = 6 };
 		enum : int { LOADF, MULS, ADDS, ADD, MUL, SETQ, ADDQ, DIVQ, NOP };
@@ -130,7 +133,10 @@ namespace qb
 		{
 			int op = NOP, d = 0, a = 0, b = 0;
 			int64_t v = 0;
-			switch (step)
+#if defined(__CUDA_ARCH__)
+			if (LOCKSTEP) __syncthreads();
+#endif
+			switch (active ? step : -1)
 			{
 			// h[m + 2, n - 1]
 			case 0: op = LOADF; v = cf_index(lambda, m + 2, n - 1); break;
@@ -194,7 +200,7 @@ namespace qb
 		}
 		// common_factor = 4 n eps + (4 n - 2) n
 		int64_t cn = int64_t(4 * n) * eps.num + int64_t(4 * n - 2) * int64_t(n) * int64_t(eps.den);
-		div_q(val, R[VAL], cn, eps.den, prec);
+		if (active) div_q(val, R[VAL], cn, eps.den, prec);
 	}
 	// h[m, n] = val + 8 h[m-3, n] + 4 h[m-2, n] - 2 h[m-1, n]; the three predecessors are handed in thread-local
 	// (p1 = h[m-1,n], p2 = h[m-2,n], p3 = h[m-3,n]); result thread-local                          (context.cpp:123-130)

@@ -99,6 +99,7 @@ extern "C"
 		case QB_ERR_BAD_ARG: return "bad argument";
 		case QB_ERR_CUDA: return "CUDA error (see qb_last_cuda_error)";
 		case QB_ERR_RANGE: return "rational dimension or spin outside the supported range";
+		case QB_ERR_ROUNDING: return "a power could not be rounded with certainty at the second Ziv level (see qb_ziv_counters)";
 		case QB_ERR_NO_MEMORY: return "device memory exhausted";
 		default: return "unknown status";
 		}
@@ -210,8 +211,78 @@ extern "C"
 			cudaGetLastError();
 			return rc;
 		}
-		return qb_sync(h);
+		rc = qb_sync(h);
+		return rc ? rc : h->e->check_rounding();
 	}
+	// ---- multi-GPU: tables of every rank gathered in one rank's HBM by peer copies -------------------------------------
+	int qb_gblock_set_sink(qb_handle* h, void* dst)
+	{
+		if (!h) return QB_ERR_BAD_ARG;
+		h->e->sink = static_cast<uint32_t*>(dst);
+		return QB_OK;
+	}
+	void* qb_device_alloc(qb_handle* h, size_t bytes)
+	{
+		void* p = nullptr;
+		if (!h || bytes == 0) return nullptr;
+		if (cudaSetDevice(h->e->device) != cudaSuccess || cudaMalloc(&p, bytes) != cudaSuccess)
+		{
+			cudaGetLastError();
+			return nullptr;
+		}
+		return p;
+	}
+	void qb_device_free(qb_handle* h, void* p)
+	{
+		if (!h || !p) return;
+		cudaSetDevice(h->e->device);
+		cudaFree(p);
+	}
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "qb_ipc_export writes a 64-byte handle");
+	int qb_ipc_export(qb_handle* h, const void* dev_ptr, unsigned char* handle64)
+	{
+		if (!h || !dev_ptr || !handle64) return QB_ERR_BAD_ARG;
+		cudaIpcMemHandle_t hd;
+		cudaSetDevice(h->e->device);
+		cudaError_t e = cudaIpcGetMemHandle(&hd, const_cast<void*>(dev_ptr));
+		if (e != cudaSuccess)
+		{
+			h->e->cuda_error = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+			cudaGetLastError();
+			return QB_ERR_CUDA;
+		}
+		std::memcpy(handle64, &hd, 64);
+		return QB_OK;
+	}
+	int qb_ipc_open(qb_handle* h, const unsigned char* handle64, void** dev_ptr)
+	{
+		if (!h || !handle64 || !dev_ptr) return QB_ERR_BAD_ARG;
+		cudaIpcMemHandle_t hd;
+		std::memcpy(&hd, handle64, 64);
+		cudaSetDevice(h->e->device);
+		cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess)
+		{
+			h->e->cuda_error = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+			cudaGetLastError();
+			return QB_ERR_CUDA;
+		}
+		return QB_OK;
+	}
+	int qb_ipc_close(qb_handle* h, void* dev_ptr)
+	{
+		if (!h || !dev_ptr) return QB_ERR_BAD_ARG;
+		cudaSetDevice(h->e->device);
+		cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+		if (e != cudaSuccess)
+		{
+			cudaGetLastError();
+			return QB_ERR_CUDA;
+		}
+		return QB_OK;
+	}
+	int qb_set_ziv_slack(qb_handle* h, int bits) { return h ? h->e->set_ziv_slack(bits) : QB_ERR_BAD_ARG; }
+	int qb_ziv_counters(qb_handle* h, uint64_t* out2) { QB_GUARDED((h && out2) ? h->e->ziv_counters(out2) : QB_ERR_BAD_ARG) }
 	int qb_op_batch(qb_handle* h, int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c,
 	                const int64_t* ia, const int64_t* ib, uint32_t* out)
 	{

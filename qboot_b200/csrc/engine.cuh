@@ -41,6 +41,9 @@ namespace qb
 		// when set, gblock_run copies every chunk's tables to this host buffer as soon as the chunk is finished (on a copy
 		// stream, overlapping the later chunks); the handle's stream then also waits for the copies
 		uint32_t* fetch_dst = nullptr;
+		// the same for every later run, for callers that keep the tables on a device: host, device or PEER-device memory
+		// (a pointer opened from another process's allocation, qb_ipc_open) -- the gather of a multi-GPU job
+		uint32_t* sink = nullptr;
 		virtual int op_batch(int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c, const int64_t* ia,
 		                     const int64_t* ib, uint32_t* out) = 0;
 		virtual int vtod_batch(int n_d, const uint32_t* d, uint32_t* out) = 0;
@@ -60,6 +63,11 @@ namespace qb
 		virtual int pmp_text_fetch(char* out) = 0;
 		virtual int pmp_info(int64_t* out4) const = 0;
 		virtual int dec_format(int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* len) = 0;
+		// Ziv loop of the powers: width of the in-doubt window (0 = default) and the counters [second-level evaluations,
+		// values still in doubt] since the handle was created
+		virtual int set_ziv_slack(int bits) = 0;
+		virtual int ziv_counters(uint64_t* out2) = 0;
+		virtual int check_rounding() = 0;
 	};
 	typedef EngineBase* (*EngineFactory)(int device, int prec);
 }  // namespace qb
@@ -138,6 +146,9 @@ namespace qb
 		Rational eps{0, 1};
 		ContextConsts<L> consts;
 		std::map<uint32_t, T> b0_cache;
+		DevBuf d_ziv;  // two counters of the powers' Ziv loop
+		int ziv_slack = QB_ZIV_SLACK;
+		uint64_t ziv_reported = 0;
 		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_qc, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms, d_fb_g;
 		DevCtx cx{};
 		int n_tables = 0, n_jobs = 0;
@@ -230,7 +241,9 @@ namespace qb
 			b0_cache.clear();
 			// upload: rho | mat | kfact | ln2e | ln4e | lnrhoe
 			size_t n1 = size_t(lam) + 1;
-			size_t bytes = sizeof(T) * (1 + n1 * n1 + n1) + (3 + n1) * sizeof(mpf<E>);
+			constexpr int E2 = ContextConsts<L>::E2;
+			const size_t ofs_w = (sizeof(T) * (1 + n1 * n1 + n1) + (3 + n1) * sizeof(mpf<E>) + 7) & ~size_t(7);
+			size_t bytes = ofs_w + 3 * sizeof(mpf<E2>) + 8;
 			if (d_consts.ensure(bytes)) return -7;
 			std::vector<uint8_t> host(bytes);
 			uint8_t* p = host.data();
@@ -245,6 +258,10 @@ namespace qb
 			put(&consts.ln4e, sizeof(mpf<E>));
 			put(&consts.lnrhoe, sizeof(mpf<E>));
 			put(consts.rhoinv.data(), sizeof(mpf<E>) * n1);
+			p = host.data() + ofs_w;
+			put(&consts.ln2w, sizeof(mpf<E2>));
+			put(&consts.ln4w, sizeof(mpf<E2>));
+			put(&consts.lnrhow, sizeof(mpf<E2>));
 			QB_CU(cudaMemcpyAsync(d_consts.p, host.data(), bytes, cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaStreamSynchronize(stream));
 			const uint8_t* d = d_consts.as<uint8_t>();
@@ -260,7 +277,50 @@ namespace qb
 			cx.ln4e = reinterpret_cast<const uint32_t*>(de + sizeof(mpf<E>));
 			cx.lnrhoe = reinterpret_cast<const uint32_t*>(de + 2 * sizeof(mpf<E>));
 			cx.rhoinv = reinterpret_cast<const uint32_t*>(de + 3 * sizeof(mpf<E>));
+			cx.ln2w = reinterpret_cast<const uint32_t*>(d + ofs_w);
+			cx.ln4w = reinterpret_cast<const uint32_t*>(d + ofs_w + sizeof(mpf<E2>));
+			cx.lnrhow = reinterpret_cast<const uint32_t*>(d + ofs_w + 2 * sizeof(mpf<E2>));
+			cx.ziv_slack = ziv_slack;
+			if (!d_ziv.p)
+			{
+				if (d_ziv.ensure(8)) return -7;
+				QB_CU(cudaMemsetAsync(d_ziv.p, 0, 8, stream));
+				QB_CU(cudaStreamSynchronize(stream));
+			}
+			cx.ziv = d_ziv.as<uint32_t>();
 			has_ctx = true;
+			return 0;
+		}
+		// -8 (QB_ERR_ROUNDING) once for every new power whose rounding stayed in doubt at the second Ziv level
+		int check_rounding() override
+		{
+			uint64_t c[2];
+			if (int rc_ = ziv_counters(c)) return rc_;
+			if (c[1] > ziv_reported)
+			{
+				ziv_reported = c[1];
+				return -8;
+			}
+			return 0;
+		}
+		int set_ziv_slack(int bits) override
+		{
+			if (bits < 0) return -4;
+			ziv_slack = bits ? bits : QB_ZIV_SLACK;
+			cx.ziv_slack = ziv_slack;
+			return 0;
+		}
+		// [0] powers re-evaluated at the second level, [1] powers whose rounding was still in doubt there
+		int ziv_counters(uint64_t* out2) override
+		{
+			out2[0] = out2[1] = 0;
+			if (!d_ziv.p) return 0;
+			uint32_t c[2] = {0, 0};
+			QB_CU(cudaSetDevice(device));
+			QB_CU(cudaMemcpyAsync(c, d_ziv.p, 8, cudaMemcpyDeviceToHost, stream));
+			QB_CU(cudaStreamSynchronize(stream));
+			out2[0] = c[0];
+			out2[1] = c[1];
 			return 0;
 		}
 		int context_get(uint32_t* rho, uint32_t* mat) const override
@@ -505,12 +565,14 @@ namespace qb
 			launches += launch_finish<L>(cx, r.t1 - r.t0, t_delta + r.t0, t_spin + r.t0, t_S + r.t0, t_P + r.t0,
 			                             d_fr.as<T>() + size_t(r.t0) * nk, d_g.as<T>() + size_t(r.t0) * dimM, d_qc.as<T>() + r.t0, st);
 		}
-		// device -> host copy of one finished chunk into fetch_dst
+		// copy of one finished chunk into fetch_dst / sink (host memory, or device memory of this or a peer GPU: the copy
+		// engine moves it over PCIe or NVLink underneath the kernels of the later chunks)
+		uint32_t* out_dst() const { return fetch_dst ? fetch_dst : sink; }
 		int copy_chunk_out(const Range& r, cudaStream_t st)
 		{
 			const size_t rec = sizeof(T) * size_t(cf_dim(int(lambda)));
-			QB_CU(cudaMemcpyAsync(reinterpret_cast<char*>(fetch_dst) + rec * size_t(r.t0), d_g.as<char>() + rec * size_t(r.t0),
-			                      rec * size_t(r.t1 - r.t0), cudaMemcpyDeviceToHost, st));
+			QB_CU(cudaMemcpyAsync(reinterpret_cast<char*>(out_dst()) + rec * size_t(r.t0), d_g.as<char>() + rec * size_t(r.t0),
+			                      rec * size_t(r.t1 - r.t0), cudaMemcpyDefault, st));
 			return 0;
 		}
 		// ---- scheduling ---------------------------------------------------------------------------------------------------
@@ -571,7 +633,7 @@ namespace qb
 					stage_finish(r, st);
 					if (int rc_ = debug_sync("k_finish")) return rc_;
 					if (int rc_ = tick(-1, st)) return rc_;
-					if (fetch_dst)
+					if (out_dst())
 						if (int rc_ = copy_chunk_out(r, st)) return rc_;
 				}
 			}
@@ -632,7 +694,7 @@ namespace qb
 					QB_CU(cudaEventRecord(EV(c, 0), mid_stream));
 					QB_CU(cudaStreamWaitEvent(fin_stream, EV(c, 0), 0));
 					stage_finish(r, fin_stream);
-					if (fetch_dst)
+					if (out_dst())
 					{
 						QB_CU(cudaEventRecord(EV(c, 1), fin_stream));
 						QB_CU(cudaStreamWaitEvent(copy_stream, EV(c, 1), 0));
@@ -645,7 +707,7 @@ namespace qb
 			QB_CU(cudaStreamWaitEvent(stream, fin_done_ev, 0));
 			QB_CU(cudaEventRecord(lo_done_ev, lo_stream));
 			QB_CU(cudaStreamWaitEvent(stream, lo_done_ev, 0));
-			if (fetch_dst)
+			if (out_dst())
 			{
 				QB_CU(cudaEventRecord(copy_done_ev, copy_stream));
 				QB_CU(cudaStreamWaitEvent(stream, copy_done_ev, 0));
@@ -711,7 +773,7 @@ namespace qb
 			size_t bytes = sizeof(T) * size_t(cf_dim(int(lambda))) * size_t(n_tables);
 			QB_CU(cudaMemcpyAsync(out, d_g.p, bytes, cudaMemcpyDeviceToHost, stream));
 			QB_CU(cudaStreamSynchronize(stream));
-			return 0;
+			return check_rounding();
 		}
 		const uint32_t* device_tables() const override { return d_g.as<uint32_t>(); }
 

@@ -240,6 +240,9 @@ namespace qb
 		std::vector<mpf<L>> kfact;  // k!
 		mpf<E> ln2e, ln4e, lnrhoe;
 		std::vector<mpf<E>> rhoinv;  // rho^-k at the extended width
+		// the logarithms once more at the second Ziv level (mpf_math.cuh)
+		static constexpr int E2 = L + QB_EXT2_LIMBS;
+		mpf<E2> ln2w, ln4w, lnrhow;
 	};
 
 	namespace detail
@@ -368,6 +371,15 @@ namespace qb
 		mpf<E> rw;
 		widen(rw, c.rho);
 		log_ext(c.lnrhoe, rw, c.ln2e);
+		{
+			constexpr int E2 = ContextConsts<L>::E2;
+			const_ln2(c.ln2w);
+			copy(c.ln4w, c.ln2w);
+			c.ln4w.exp += 1;
+			mpf<E2> rw2;
+			widen(rw2, c.rho);
+			log_ext(c.lnrhow, rw2, c.ln2w);
+		}
 		// rho^-k = exp(-k ln rho), each from its own exponential (no error accumulation)
 		c.rhoinv.resize(size_t(n1));
 		for (int k = 0; k <= lam; ++k)

@@ -75,7 +75,8 @@ namespace qb
 		k_rho_to_z<QB_L><<<blocks(int64_t(n_tables) * (lambda + 1)), threads, 0, st>>>(cx, n_tables, delta, spin, fr, g, qc);
 		for (int n = 1; n <= lambda / 2; ++n)
 		{
-			k_offdiag_val<QB_L><<<blocks(int64_t(n_tables) * (lambda - 2 * n + 1)), threads, 0, st>>>(cx, n_tables, n, S, P, qc, g);
+			k_offdiag_val<QB_L><<<unsigned((int64_t(n_tables) * (lambda - 2 * n + 1) + QB_OFFDIAG_THREADS - 1) / QB_OFFDIAG_THREADS), QB_OFFDIAG_THREADS, 0, st>>>(
+			    cx, n_tables, n, S, P, qc, g);
 			k_offdiag_close<QB_L><<<blocks(n_tables), threads, 0, st>>>(cx, n_tables, n, g);
 			count += 2;
 		}

@@ -90,10 +90,10 @@ namespace qb
 		case 11: add_q(r, x, p, uint32_t(q), prec); break;
 		case 12: set_q(r, p, uint32_t(q), prec); break;
 		case 13:  // rho^y
-			pow_from_log<L>(r, *reinterpret_cast<const mpf<E>*>(cx.lnrhoe), y, *reinterpret_cast<const mpf<E>*>(cx.ln2e), prec);
+			pow_ziv<L>(r, cx.lnrhoe, cx.ln2e, cx.lnrhow, cx.ln2w, y, prec, cx.ziv_slack, cx.ziv);
 			break;
 		case 14:  // 4^x
-			pow_from_log<L>(r, *reinterpret_cast<const mpf<E>*>(cx.ln4e), x, *reinterpret_cast<const mpf<E>*>(cx.ln2e), prec);
+			pow_ziv<L>(r, cx.ln4e, cx.ln2e, cx.ln4w, cx.ln2w, x, prec, cx.ziv_slack, cx.ziv);
 			break;
 		case 18: si_sub(r, p, x, prec); break;
 		case 20: sub_q(r, x, p, uint32_t(q), prec); break;

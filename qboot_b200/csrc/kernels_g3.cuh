@@ -48,21 +48,24 @@ namespace qb
 		}
 	}
 
+	constexpr int QB_OFFDIAG_THREADS = 256;
 	template <int L>
-	__global__ void __launch_bounds__(128) k_offdiag_val(DevCtx cx, int n_tables, int n, const mpf<L>* __restrict__ S,
-	                                                     const mpf<L>* __restrict__ P, const mpf<L>* __restrict__ qc, mpf<L>* g)
+	__global__ void __launch_bounds__(QB_OFFDIAG_THREADS) k_offdiag_val(DevCtx cx, int n_tables, int n, const mpf<L>* __restrict__ S,
+	                                                                    const mpf<L>* __restrict__ P, const mpf<L>* __restrict__ qc, mpf<L>* g)
 	{
 		const int lambda = int(cx.lambda), dimM = cf_dim(lambda), cnt = lambda - 2 * n + 1;
 		const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-		const int t = gid / cnt, m = gid - t * cnt;
-		if (t >= n_tables) return;
+		int t = gid / cnt;
+		const int m = gid - t * cnt;
+		const bool active = t < n_tables;  // idle threads keep the barriers of the lockstep interpreter company
+		if (!active) t = 0;
 		mpf<L>* f = g + size_t(t) * dimM;
 		mpf<L> lS, lP, q4, val;
 		copy(lS, S[t]);
 		copy(lP, P[t]);
 		copy(q4, qc[t]);
-		offdiag_val(val, f, 1, lambda, m, n, lS, lP, q4, cx.eps, cx.prec);
-		copy(f[cf_index(lambda, m, n)], val);
+		offdiag_val<L, true>(val, f, 1, lambda, m, n, lS, lP, q4, cx.eps, cx.prec, active);
+		if (active) copy(f[cf_index(lambda, m, n)], val);
 	}
 
 	template <int L>

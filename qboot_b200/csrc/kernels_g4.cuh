@@ -38,7 +38,7 @@ namespace qb
 		mpf<L> q0, q, r;
 		copy(q0, delta[t]);
 		copy(pw[size_t(t) * row + np], q0);
-		pow_from_log<L>(r, *reinterpret_cast<const mpf<E>*>(cx.ln4e), q0, *reinterpret_cast<const mpf<E>*>(cx.ln2e), cx.prec);
+		pow_ziv<L>(r, cx.ln4e, cx.ln2e, cx.ln4w, cx.ln2w, q0, cx.prec, cx.ziv_slack, cx.ziv);
 		copy(pw[size_t(t) * row], r);
 		// X = exp(q0 ln rho) in the extended format
 		mpf<E> X, lnr, l2, qe, te, corr, one, v;
@@ -48,6 +48,16 @@ namespace qb
 		fast::mul(te, qe, lnr, pe);
 		exp_ext(X, te, l2);
 		narrow(r, X, cx.prec);
+		// every power is rounded from an extended value: a rounding in doubt (ziv_safe) is redone from a full
+		// exponential at the second-level width
+		auto redo = [&](mpf<L>& out, const mpf<L>& y) {
+			constexpr int E2 = L + QB_EXT2_LIMBS;
+			ziv_count(cx.ziv, 0);
+			if (!pow_from_log<L, QB_EXT2_LIMBS>(out, *reinterpret_cast<const mpf<E2>*>(cx.lnrhow), y, *reinterpret_cast<const mpf<E2>*>(cx.ln2w),
+			                                    cx.prec))
+				ziv_count(cx.ziv, 1);
+		};
+		if (!ziv_safe(X, cx.prec, cx.ziv_slack)) redo(r, q0);
 		copy(pw[size_t(t) * row + 1], r);
 		set_si(one, 1, pe);
 		copy(q, q0);
@@ -69,6 +79,7 @@ namespace qb
 				fast::mul(v, v, corr, pe);
 			}
 			narrow(r, v, cx.prec);
+			if (!ziv_safe(v, cx.prec, cx.ziv_slack + 2)) redo(r, q);  // three more roundings and the dropped eta^2 term: 2 bits wider
 			copy(pw[size_t(t) * row + 1 + k], r);
 		}
 	}
@@ -82,7 +93,7 @@ namespace qb
 		mpf<L> md, p4;
 		copy(md, d[i]);
 		neg(md);
-		pow_from_log<L>(p4, *reinterpret_cast<const mpf<E>*>(cx.ln4e), md, *reinterpret_cast<const mpf<E>*>(cx.ln2e), cx.prec);
+		pow_ziv<L>(p4, cx.ln4e, cx.ln2e, cx.ln4w, cx.ln2w, md, cx.prec, cx.ziv_slack, cx.ziv);
 		v_to_d_table(v + size_t(i) * cf_dim(int(cx.lambda)), 1, int(cx.lambda), d[i], p4, cx.prec);
 	}
 

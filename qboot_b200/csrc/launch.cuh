@@ -22,6 +22,14 @@ namespace qb
 		const uint32_t* lnrhoe;
 		const uint32_t* kfact;    // k!, k = 0..lambda, mpf<L>
 		const uint32_t* rhoinv;   // rho^-k, k = 0..lambda, mpf<L + QB_EXT_LIMBS>
+		// second Ziv level of the powers (mpf_math.cuh): the logarithms at L + QB_EXT2_LIMBS limbs, the width (in bits of the
+		// extended result's last place) inside which a rounding counts as in doubt, and two device counters
+		// ([0] second-level evaluations, [1] values still in doubt)
+		const uint32_t* ln2w;
+		const uint32_t* ln4w;
+		const uint32_t* lnrhow;
+		int ziv_slack;
+		uint32_t* ziv;
 	};
 
 	// a series job: one run of the recurrence at (Delta', spin, S, P)

@@ -3,8 +3,12 @@
 // The reference calls mpfr_pow / mpfr_ui_pow on the table path (src/hor_recursion.cpp:43 `pow(4, Delta)`,
 // include/qboot/algebra/real_function.hpp:262 `pow(x, pow_)`), which are correctly rounded.  Here x^y is evaluated as
 // exp(y * ln x) in an extended format of E = L + QB_EXT_LIMBS limbs (ln x and ln 2 are supplied at that width) and
-// rounded once to `prec` bits.  The extended result carries a relative error below 2^-(32L + 50), so the final
-// rounding equals the correct rounding unless the exact value lies within that distance of a rounding boundary.
+// rounded once to `prec` bits.  The extended result carries an error below 2^46 units of ITS last place, so the final
+// rounding equals the correct rounding unless the exact value lies within that distance of a rounding boundary (a
+// midpoint between two prec-bit numbers).  That case is DETECTED (ziv_safe: the discarded bits read 1000...0x or
+// 0111...1x down to bit QB_ZIV_SLACK) and the value is recomputed at E = L + QB_EXT2_LIMBS limbs -- Ziv's strategy,
+// which is what makes mpfr_pow correctly rounded; x^y with rational x, y is never exactly a midpoint unless it is
+// exactly representable, so the second level settles everything but a 2^-140 event, which is reported, not hidden.
 #pragma once
 
 #include "fastops.cuh"
@@ -13,6 +17,11 @@
 #ifndef QB_EXT_LIMBS
 #define QB_EXT_LIMBS 3
 #endif
+#ifndef QB_EXT2_LIMBS
+#define QB_EXT2_LIMBS 6  // second Ziv level
+#endif
+// error bound of an extended result, in bits of its own last place, with margin (analysis: < 2^46)
+#define QB_ZIV_SLACK 56
 
 namespace qb
 {
@@ -36,6 +45,20 @@ namespace qb
 			return;
 		}
 		round_to<L, E>(r, a.sk, a.exp, a.m, 0u, prec);
+	}
+	// Can the rounding of `a` (E limbs, true value within 2^slack units of a's last place) to prec bits be trusted?
+	// Bit G - 1 of the mantissa (G = 32 E - prec discarded bits) is the round bit; the rounding is in doubt iff the
+	// bits below it, down to bit `slack`, all differ from it: 1000...0x / 0111...1x, a value next to a midpoint.
+	template <int E>
+	QB_HD QB_INLINE bool ziv_safe(const mpf<E>& a, int prec, int slack)
+	{
+		if (kind(a) != K_REG) return true;
+		const int G = 32 * E - prec;
+		if (slack >= G - 1) return false;
+		const uint32_t rb = (a.m[(G - 1) >> 5] >> ((G - 1) & 31)) & 1u;
+		for (int i = G - 2; i >= slack; --i)
+			if (((a.m[i >> 5] >> (i & 31)) & 1u) == rb) return true;
+		return false;
 	}
 	// top 53 bits as a double (truncated); zero/regular only
 	template <int E>
@@ -101,13 +124,14 @@ namespace qb
 		r.exp += int32_t(k);
 	}
 
-	// r = RN_prec(exp(y * lnx)),  lnx and ln2 given in E = L + QB_EXT_LIMBS limbs
-	template <int L>
+	// r = RN_prec(exp(y * lnx)),  lnx and ln2 given in E = L + X limbs.  Returns false when the rounding is in doubt at
+	// this width (see ziv_safe): the caller repeats the call with the wider constants.
+	template <int L, int X = QB_EXT_LIMBS>
 	// r, y thread-local; lnx, ln2 anywhere
-	QB_HD QB_NOINLINE void pow_from_log(mpf<L>& r, const mpf<L + QB_EXT_LIMBS>& lnx, const mpf<L>& y,
-	                        const mpf<L + QB_EXT_LIMBS>& ln2, int prec)
+	QB_HD QB_NOINLINE bool pow_from_log(mpf<L>& r, const mpf<L + X>& lnx, const mpf<L>& y, const mpf<L + X>& ln2, int prec,
+	                                    int slack = QB_ZIV_SLACK)
 	{
-		constexpr int E = L + QB_EXT_LIMBS;
+		constexpr int E = L + X;
 		// lnx / ln2 may live in global memory: stage them into thread-local records once, they are reused below
 		mpf<E> ye, t, v, lx, l2;
 		copy(lx, lnx);
@@ -116,27 +140,47 @@ namespace qb
 		fast::mul(t, ye, lx, 32 * E);
 		exp_ext(v, t, l2);
 		narrow(r, v, prec);
+		return ziv_safe(v, prec, slack);
+	}
+
+	// Ziv's loop for x^y: first level at L + QB_EXT_LIMBS limbs (lnx1, ln2_1), second at L + QB_EXT2_LIMBS (lnx2, ln2_2).
+	// counters (may be null): [0] += second-level evaluations, [1] += values still in doubt after it (reported by the engine
+	// as QB_ERR_ROUNDING: the result is then correctly rounded only with probability 1 - 2^-140).
+	QB_HD QB_INLINE void ziv_count(uint32_t* counters, int which)
+	{
+		if (!counters) return;
+#if defined(__CUDA_ARCH__)
+		atomicAdd(counters + which, 1u);
+#else
+		counters[which] += 1u;
+#endif
+	}
+	template <int L>
+	QB_HD QB_NOINLINE void pow_ziv(mpf<L>& r, const uint32_t* lnx1, const uint32_t* ln2_1, const uint32_t* lnx2, const uint32_t* ln2_2,
+	                               const mpf<L>& y, int prec, int slack, uint32_t* counters)
+	{
+		constexpr int E1 = L + QB_EXT_LIMBS, E2 = L + QB_EXT2_LIMBS;
+		if (pow_from_log<L, QB_EXT_LIMBS>(r, *reinterpret_cast<const mpf<E1>*>(lnx1), y, *reinterpret_cast<const mpf<E1>*>(ln2_1), prec, slack))
+			return;
+		ziv_count(counters, 0);
+		if (pow_from_log<L, QB_EXT2_LIMBS>(r, *reinterpret_cast<const mpf<E2>*>(lnx2), y, *reinterpret_cast<const mpf<E2>*>(ln2_2), prec))
+			return;
+		ziv_count(counters, 1);
 	}
 
 #if !defined(__CUDACC__)
-	// test harness hook (tests/hostemu): consts = [ln2 (E+2 words), lnx (E+2 words)]
+	// test harness hook (tests/hostemu): consts = [ln2 (E+2 words), lnx (E+2 words)]; p = Ziv slack override (0: default).
+	// A rounding in doubt at this width is reported by returning false: the harness then has no answer (the engine
+	// recomputes with the wider constants, see k_pow_fix).
 	template <int L>
 	bool hostemu_math(int prec, int op, const mpf<L>& x, const mpf<L>& y, int64_t p, const uint32_t* consts, mpf<L>& r)
 	{
 		constexpr int E = L + QB_EXT_LIMBS;
 		if (!consts) return false;
 		const mpf<E>* c = reinterpret_cast<const mpf<E>*>(consts);
-		(void)p;
-		if (op == 13)
-		{
-			pow_from_log<L>(r, c[1], y, c[0], prec);  // x^y with ln x = c[1]
-			return true;
-		}
-		if (op == 14)
-		{
-			pow_from_log<L>(r, c[1], x, c[0], prec);  // p^x with ln p = c[1]
-			return true;
-		}
+		const int slack = p > 0 ? int(p) : QB_ZIV_SLACK;
+		if (op == 13) return pow_from_log<L>(r, c[1], y, c[0], prec, slack);  // x^y with ln x = c[1]
+		if (op == 14) return pow_from_log<L>(r, c[1], x, c[0], prec, slack);  // p^x with ln p = c[1]
 		if (op == 15)
 		{
 			mpf<E> xe, v;

@@ -59,7 +59,12 @@ namespace
 			case 13:  // pow(x, y) with x > 0 given ln(x) in consts (extended precision)
 			case 14:  // ui_pow
 			case 15:  // exp
-				if (!qb::hostemu_math<L>(prec, op, x, y, p, consts, r)) return -2;
+				// false: no constants supplied, or (13 / 14) the rounding is in doubt at this width -- r is set all the same
+				if (!qb::hostemu_math<L>(prec, op, x, y, p, consts, r))
+				{
+					O[i] = r;
+					return -2;
+				}
 				break;
 			default: return -1;
 			}

@@ -240,6 +240,38 @@ def test_bench_workload_vs_reference(ref):
     assert len(keys) >= 80 and not bad, bad
 
 
+def test_pow_second_ziv_level_is_correctly_rounded(ref):
+    """x^y is exp(y ln x) at 96 guard bits with a second level at 192 when the rounding is in doubt.  A real doubt has
+    probability 2^-40 per power, so the retry is forced by construction: the in-doubt window is widened until about one
+    power in eight takes the second level; results must still be MPFR's (mpfr_pow is correctly rounded), the counters must
+    show that the second level ran and that nothing stayed in doubt."""
+    from tests.golden.make_golden import rnd_num
+
+    for prec, n_max, lam in ((1024, 60, 9), (600, 40, 7)):
+        eng = _engine(prec, n_max, lam)
+        guard = 32 * (qb.nlimbs(prec) + 3) - prec
+        rng = random.Random(prec)
+        ys = np.stack([qb.from_fraction(Fraction(rng.randint(1, 10**8), rng.randint(10**5, 10**6)), prec) for _ in range(400)])
+        rho = np.tile(eng.context_consts()[0], (len(ys), 1))
+        want_rho = ref.op("pow", prec, a=rho, b=ys)
+        want_4 = ref.op("ui_pow", prec, a=ys, ia=np.full(len(ys), 4, dtype=np.int64))
+        assert eng.ziv_counters() == (0, 0)
+        assert np.array_equal(eng.op(OPS["pow"], b=ys), want_rho) and np.array_equal(eng.op(OPS["ui_pow"], a=ys), want_4)
+        assert eng.ziv_counters() == (0, 0)          # default window: no power of this sample is in doubt
+        eng.set_ziv_slack(guard - 4)                 # in doubt when the three bits below the round bit all differ from it
+        assert np.array_equal(eng.op(OPS["pow"], b=ys), want_rho) and np.array_equal(eng.op(OPS["ui_pow"], a=ys), want_4)
+        redone, undecided = eng.ziv_counters()
+        assert 40 <= redone <= 200 and undecided == 0, (redone, undecided)
+        # the table pipeline (k_pow: 4^Delta and rho^(Delta - k), k = 0..lambda) under the same window
+        spin = np.array([0, 1, 2, 3, 4, 6], dtype=np.uint32)
+        delta = np.stack([qb.from_fraction(Fraction(rng.randint(10**6, 10**8), 10**6), prec) for _ in spin])
+        z = qb.zeros(len(spin), prec)
+        got = eng.gblock(spin, delta, z, z)
+        assert eng.ziv_counters()[0] > redone and eng.ziv_counters()[1] == 0
+        assert np.array_equal(got, ref.gblock(prec, n_max, lam, "3", delta, spin, z, z))
+        eng.close()
+
+
 # ---- the PMP half of the path: planner + device assembly / pack / decimal text through the C++ facade -------------------
 def _same_dirs(a, b):
     import filecmp

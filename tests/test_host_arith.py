@@ -246,3 +246,48 @@ def test_short_product_boundaries(hostemu, ref, prec):
         got = _fast(hostemu, FAST[name], prec, **kw)
         bad = [i for i in range(len(want)) if not np.array_equal(want[i], got[i])]
         assert not bad, (name, bad[:5])
+
+
+def test_ziv_window_flags_exactly_the_values_next_to_a_midpoint(hostemu, ref):
+    """pow_from_log reports a rounding as in doubt iff the extended value lies inside the window around a midpoint between
+    two prec-bit numbers (mpf_math.cuh: ziv_safe).  With the window widened to 1/16 ulp on either side the flagged set
+    must be exactly the set found from MPFR's value of the same power at 256 more bits."""
+    import math
+    import random
+    from fractions import Fraction
+
+    import qboot_b200 as qb
+    from tests.util import OPS
+
+    prec, wide = 600, 600 + 256
+    rho = ref.op("si_sub", prec, a=ref.op("sqrt", prec, a=ref.from_int_exp(0, 8, 0, prec)), ia=[3])[0]
+    ce = _ext_consts(ref, prec, rho)
+    E2 = ref.nlimbs(prec) + 3 + 2
+    ln2, lnrho = ce[:E2], ce[2 * E2:]
+    guard = 32 * (ref.nlimbs(prec) + 3) - prec
+    rng = random.Random(7)
+    ys = [Fraction(rng.randint(1, 10**8), rng.randint(10**5, 10**6)) for _ in range(160)]
+    rho_w = qb.from_fraction(qb.to_fraction(rho, prec), wide)
+    flagged = truth = 0
+    for y in ys:
+        yr = qb.from_fraction(y, prec)
+        out = np.zeros((1, words(prec)), dtype=np.uint32)
+        rc = hostemu.qbh_op(prec, OPS["pow"], 1, P(rho[None, :].copy()), P(yr[None, :].copy()), None,
+                            P(np.array([guard - 4], dtype=np.int64)), None, P(out), P(np.concatenate([ln2, lnrho])))
+        assert rc in (0, -2)
+        v = qb.to_fraction(ref.op("pow", wide, a=rho_w, b=qb.from_fraction(qb.to_fraction(yr, prec), wide))[0], wide)
+        e = v.numerator.bit_length() - v.denominator.bit_length()
+        while Fraction(2) ** (e - 1) > v:
+            e -= 1
+        while Fraction(2) ** e <= v:
+            e += 1
+        f = v / Fraction(2) ** (e - prec)
+        f -= math.floor(f)
+        # f in [7/16, 9/16): round bit 1 followed by 000, or round bit 0 followed by 111
+        near = Fraction(7, 16) <= f < Fraction(9, 16)
+        assert (rc == -2) == near, (y, float(f), rc)
+        flagged += rc == -2
+        truth += near
+        # whatever the window says, the value itself is MPFR's
+        assert np.array_equal(out[0], ref.op("pow", prec, a=rho, b=yr)[0])
+    assert flagged == truth and 5 <= flagged <= 40
