@@ -12,7 +12,7 @@ from fractions import Fraction
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqboot_b200.so")
+LIB_PATH = os.environ.get("QB_LIB_PATH") or os.path.join(_HERE, "libqboot_b200.so")  # QB_LIB_PATH: development builds
 
 # every symbol include/qboot_b200.h declares
 SYMBOLS = (

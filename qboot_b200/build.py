@@ -69,7 +69,10 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
     for L in LIMBS:
         for g in KGROUPS:
-            add(f"kernels_L{L}_g{g}", "kernel_inst.cu", [f"-DQB_L={L}", f"-DQB_KGROUP={g}", f"-DQB_L_FIRST={LIMBS[0]}"])
+            # QB_NVCC_EXTRA_G<g>: extra flags for one kernel group (development: try a launch configuration without
+            # rebuilding the other groups)
+            extra = os.environ.get(f"QB_NVCC_EXTRA_G{g}", "").split()
+            add(f"kernels_L{L}_g{g}", "kernel_inst.cu", [f"-DQB_L={L}", f"-DQB_KGROUP={g}", f"-DQB_L_FIRST={LIMBS[0]}", *extra])
     for L in LIMBS:
         add(f"engine_L{L}", "engine_inst.cu", [f"-DQB_L={L}"])
     add("capi", "capi.cu", ["-DQB_L_LIST=" + " ".join(f"X({L})" for L in LIMBS)])

@@ -478,9 +478,9 @@ namespace qb
 				n_chunks = n > chunk ? int((n + chunk - 1) / chunk) : 1;
 				chunk_t.assign(size_t(n_chunks) + 1, n);
 				for (int c = 0; c < n_chunks; ++c) chunk_t[size_t(c)] = int(std::min<int64_t>(n, chunk * c));
-				// front groups: whole chunks, about two waves of k_series (one thread per job, 4 CTAs of 128 per SM) each
+				// front groups: whole chunks, about three waves of k_series (one thread per job, one CTA of 384 per SM) each
 				static const int env_front = std::getenv("QB_FRONT") ? std::max(256, std::atoi(std::getenv("QB_FRONT"))) : 0;
-				const int64_t front = env_front ? env_front : int64_t(2) * sm_count * 4 * 128;
+				const int64_t front = env_front ? env_front : int64_t(3) * sm_count * 384;
 				group_c.assign(1, 0);
 				for (int c = 1; c <= n_chunks; ++c)
 					if (c == n_chunks || chunk_t[size_t(c)] - chunk_t[size_t(group_c.back())] >= front) group_c.push_back(c);
@@ -577,7 +577,7 @@ namespace qb
 		}
 		// ---- scheduling ---------------------------------------------------------------------------------------------------
 		// The batch is cut into chunks (table ranges; the scaled-coefficient scratch is one chunk-sized slot) and the chunks
-		// are gathered into FRONT GROUPS of about two waves of the series kernel.  The front stages -- recurrence
+		// are gathered into FRONT GROUPS of about three waves of the series kernel.  The front stages -- recurrence
 		// coefficients, series recurrence, powers: one thread per job / table, a long dependent chain each -- are launched
 		// once per group so that every scheduler has its four warps; the wide stages run chunk by chunk:
 		//   lo_stream   coefficients + series + powers of every group, in order

@@ -22,6 +22,96 @@ namespace qb
 {
 	namespace fast
 	{
+		// ---- cold paths ---------------------------------------------------------------------------------------------------
+		// The generic routines of mpf.cuh index their operands dynamically, so any record handed to them by reference is
+		// forced into thread-local MEMORY for its whole lifetime -- also on the hot path, where the call is never taken
+		// (measured: 96 local loads / stores per mul_small, 130 + 154 per fma, 13 % of all instructions of k_series).  The
+		// fall-backs therefore work on copies made inside the cold branch; the caller's records stay in registers.
+		// QB_COLD_COPY = 0 hands the caller's records over directly.  Which is faster is decided per kernel group by measurement
+		// (kernel_inst.cu): the copies win where registers are plentiful (k_series at 170 registers: -19 %), and lose in the
+		// 128-register kernels (k_scale / k_horner +4 %, transverse recursion +11 %, coefficients +21 %), whose operands are
+		// better off in L1-resident local memory than competing for registers.
+#ifndef QB_COLD_COPY
+#define QB_COLD_COPY 0
+#endif
+		template <int L>
+		QB_HD QB_INLINE void cold_mul(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec)
+		{
+#if !QB_COLD_COPY
+			qb::mul(r, a, b, prec);
+			return;
+#endif
+			mpf<L> a2, b2, r2;
+			copy(a2, a);
+			copy(b2, b);
+			qb::mul(r2, a2, b2, prec);
+			copy(r, r2);
+		}
+		template <int L>
+		QB_HD QB_INLINE void cold_fma(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, const mpf<L>& c, int prec)
+		{
+#if !QB_COLD_COPY
+			qb::fma(r, a, b, c, prec);
+			return;
+#endif
+			mpf<L> a2, b2, c2, r2;
+			copy(a2, a);
+			copy(b2, b);
+			copy(c2, c);
+			qb::fma(r2, a2, b2, c2, prec);
+			copy(r, r2);
+		}
+		template <int L>
+		QB_HD QB_INLINE void cold_add(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec, bool negate_b)
+		{
+#if !QB_COLD_COPY
+			qb::add(r, a, b, prec, negate_b);
+			return;
+#endif
+			mpf<L> a2, b2, r2;
+			copy(a2, a);
+			copy(b2, b);
+			qb::add(r2, a2, b2, prec, negate_b);
+			copy(r, r2);
+		}
+		template <int L>
+		QB_HD QB_INLINE void cold_div(mpf<L>& r, const mpf<L>& a, const mpf<L>& b, int prec)
+		{
+#if !QB_COLD_COPY
+			qb::div(r, a, b, prec);
+			return;
+#endif
+			mpf<L> a2, b2, r2;
+			copy(a2, a);
+			copy(b2, b);
+			qb::div(r2, a2, b2, prec);
+			copy(r, r2);
+		}
+		template <int L>
+		QB_HD QB_INLINE void cold_mul_si(mpf<L>& r, const mpf<L>& a, int64_t v, int prec)
+		{
+#if !QB_COLD_COPY
+			qb::mul_si(r, a, v, prec);
+			return;
+#endif
+			mpf<L> a2, r2;
+			copy(a2, a);
+			qb::mul_si(r2, a2, v, prec);
+			copy(r, r2);
+		}
+		template <int L>
+		QB_HD QB_INLINE void cold_add_si(mpf<L>& r, const mpf<L>& a, int64_t v, int prec)
+		{
+#if !QB_COLD_COPY
+			qb::add_si(r, a, v, prec);
+			return;
+#endif
+			mpf<L> a2, r2;
+			copy(a2, a);
+			qb::add_si(r2, a2, v, prec);
+			copy(r, r2);
+		}
+
 		// ---- carry-chain primitives ------------------------------------------------------------------------------------
 		// On the device these are PTX mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into ONE IMAD.WIDE.U32.X per limb
 		// product with the carry travelling in a predicate; the host build (and -DQB_EMULATE_CARRY_CHAINS, used by the
@@ -673,7 +763,7 @@ namespace qb
 		{
 			if ((a.sk & 3u) != K_REG || (b.sk & 3u) != K_REG)
 			{
-				qb::mul(r, a, b, prec);
+				cold_mul(r, a, b, prec);
 				return;
 			}
 			mul_strided<L, 1>(r, a.sk, a.exp, a.m, b, prec);
@@ -697,10 +787,10 @@ namespace qb
 		{
 			if ((a.sk & 3u) != K_REG || (b.sk & 3u) != K_REG || (c.sk & 3u) != K_REG)
 			{
-				qb::fma(r, a, b, c, prec);
+				cold_fma(r, a, b, c, prec);
 				return;
 			}
-			if (!fma_strided<L, 1>(r, a.sk, a.exp, a.m, b, c, prec)) qb::fma(r, a, b, c, prec);
+			if (!fma_strided<L, 1>(r, a.sk, a.exp, a.m, b, c, prec)) cold_fma(r, a, b, c, prec);
 		}
 
 		// r = RN(a + b) (negate_b: a - b)
@@ -709,7 +799,7 @@ namespace qb
 		{
 			if ((a.sk & 3u) != K_REG || (b.sk & 3u) != K_REG)
 			{
-				qb::add(r, a, b, prec, negate_b);
+				cold_add(r, a, b, prec, negate_b);
 				return;
 			}
 			uint32_t X[L + 2];
@@ -719,7 +809,7 @@ namespace qb
 			mpf<L> bb;
 			copy(bb, b);
 			if (negate_b) bb.sk ^= SIGN_BIT;
-			if (!addround<L>(r, a.sk, a.exp, X, 0u, bb, prec)) qb::add(r, a, b, prec, negate_b);
+			if (!addround<L>(r, a.sk, a.exp, X, 0u, bb, prec)) cold_add(r, a, b, prec, negate_b);
 		}
 
 		// r = RN(a * v), 0 < |v| < 2^32   (mpfr_mul_ui / mpfr_mul_si with a small multiplier)
@@ -729,7 +819,7 @@ namespace qb
 			const uint64_t u = v < 0 ? uint64_t(0) - uint64_t(v) : uint64_t(v);
 			if ((a.sk & 3u) != K_REG || u == 0 || (u >> 32) != 0)
 			{
-				qb::mul_si(r, a, v, prec);
+				cold_mul_si(r, a, v, prec);
 				return;
 			}
 			uint32_t X[L + 2];
@@ -744,7 +834,83 @@ namespace qb
 			}
 			X[L + 1] = uint32_t(cy);
 			const uint32_t sgn = (a.sk ^ (v < 0 ? SIGN_BIT : 0u)) & SIGN_BIT;
-			if (!round_frame<L>(r, sgn, a.exp + 32, X, 0u, prec)) qb::mul_si(r, a, v, prec);
+			if (!round_frame<L>(r, sgn, a.exp + 32, X, 0u, prec)) cold_mul_si(r, a, v, prec);
+		}
+
+		// (hi:lo) << t, upper word, 0 <= t <= 32
+		QB_HD QB_INLINE uint32_t shl_pair32(uint32_t hi, uint32_t lo, int t)
+		{
+#if defined(__CUDA_ARCH__)
+			return __funnelshift_lc(lo, hi, t);
+#else
+			return uint32_t((((uint64_t(hi) << 32) | lo) << t) >> 32);
+#endif
+		}
+		// s <- RN(RN(s * n) + c): one step of the reference's Horner evaluation with an integer argument (Polynomial::eval,
+		// include/qboot/algebra/polynomial.hpp:66-83: mul_ui, then add, each rounded) as ONE pass: the product is rounded in
+		// place as an integer (its dropped bits all sit in the two lowest limbs), shifted once into the normalised frame of
+		// the addition and handed to addround -- no intermediate record, no second normalisation.  s, c regular, 0 < n < 2^32.
+		// Returns false (s untouched) when addround declines; the caller then takes mul_small + add.
+		template <int L>
+		QB_HD QB_INLINE bool horner_step(mpf<L>& s, uint32_t n, const mpf<L>& c, int prec)
+		{
+			constexpr int N = L + 2;
+			// T[0 .. L] = s.m * n
+			uint32_t T[L + 1];
+			{
+				uint64_t cy = 0;
+#pragma unroll
+				for (int j = 0; j < L; ++j)
+				{
+					cy += uint64_t(s.m[j]) * n;
+					T[j] = uint32_t(cy);
+					cy >>= 32;
+				}
+				T[L] = uint32_t(cy);
+			}
+			// the product has 32 L + nb bits; keep prec of them: round away the k = nb + (32 L - prec) lowest (k <= 63)
+			int nb = T[L] ? 32 - clz32(T[L]) : 0;
+			const int k = nb + (32 * L - prec);
+			if (k > 0)
+			{
+				uint64_t low = (uint64_t(T[1]) << 32) | T[0];
+				const uint64_t mask = (uint64_t(1) << k) - 1u, half = uint64_t(1) << (k - 1);
+				const uint64_t rem = low & mask;
+				const bool up = rem > half || (rem == half && ((low >> k) & 1u));  // k <= 63: bit k is inside `low`
+				low &= ~mask;
+				if (up)
+				{
+					const uint64_t inc = uint64_t(1) << k, sum = low + inc;
+					if (sum < inc)
+					{
+						// the carry leaves the two lowest limbs (probability ~2^-(64 - k))
+						bool cyb = true;
+#pragma unroll
+						for (int j = 2; j <= L; ++j)
+						{
+							T[j] += cyb ? 1u : 0u;
+							cyb = cyb && T[j] == 0u;
+						}
+						nb = T[L] ? 32 - clz32(T[L]) : 0;
+					}
+					low = sum;
+				}
+				T[0] = uint32_t(low);
+				T[1] = uint32_t(low >> 32);
+			}
+			// normalised frame of N = L + 2 limbs: F = T << (64 - nb)
+			uint32_t F[N];
+			const int t = 32 - nb;  // 0 .. 32
+#pragma unroll
+			for (int j = 0; j < N; ++j)
+			{
+				const uint32_t hi = (j >= 1) ? T[j - 1] : 0u, lo = (j >= 2) ? T[j - 2] : 0u;
+				F[j] = shl_pair32(hi, lo, t);
+			}
+			mpf<L> r;
+			if (!addround<L>(r, s.sk, s.exp + nb, F, 0u, c, prec)) return false;
+			copy(s, r);
+			return true;
 		}
 
 		// r = RN(a + v) for a small integer v
@@ -754,7 +920,7 @@ namespace qb
 			const uint64_t u = v < 0 ? uint64_t(0) - uint64_t(v) : uint64_t(v);
 			if ((a.sk & 3u) != K_REG || u == 0 || (u >> 32) != 0)
 			{
-				qb::add_si(r, a, v, prec);
+				cold_add_si(r, a, v, prec);
 				return;
 			}
 			// v as a normalised record (exact: prec >= 64)
@@ -769,7 +935,7 @@ namespace qb
 			X[0] = X[1] = 0u;
 #pragma unroll
 			for (int j = 0; j < L; ++j) X[2 + j] = a.m[j];
-			if (!addround<L>(r, a.sk, a.exp, X, 0u, t, prec)) qb::add_si(r, a, v, prec);
+			if (!addround<L>(r, a.sk, a.exp, X, 0u, t, prec)) cold_add_si(r, a, v, prec);
 		}
 
 		// ---- division ----------------------------------------------------------------------------------------------------
@@ -824,7 +990,7 @@ namespace qb
 		{
 			if ((a.sk & 3u) != K_REG || (b.sk & 3u) != K_REG)
 			{
-				qb::div(r, a, b, prec);
+				cold_div(r, a, b, prec);
 				return;
 			}
 			constexpr int LP = (L + 1) & ~1;
@@ -920,7 +1086,7 @@ namespace qb
 			X[0] = 0u;
 #pragma unroll
 			for (int i = 0; i <= L; ++i) X[1 + i] = Q[i];
-			if (!round_frame<L>(r, (a.sk ^ b.sk) & SIGN_BIT, e, X, st, prec)) qb::div(r, a, b, prec);
+			if (!round_frame<L>(r, (a.sk ^ b.sk) & SIGN_BIT, e, X, st, prec)) cold_div(r, a, b, prec);
 		}
 	}  // namespace fast
 }  // namespace qb

@@ -5,6 +5,9 @@
 #error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..5>"
 #endif
 #include <cstdlib>
+#if QB_KGROUP == 1 && !defined(QB_COLD_COPY)
+#define QB_COLD_COPY 1  // see fastops.cuh, "cold paths"
+#endif
 #if QB_KGROUP == 0
 #include "kernels_g0.cuh"
 #elif QB_KGROUP == 1

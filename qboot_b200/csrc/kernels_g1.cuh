@@ -51,7 +51,13 @@ namespace qb
 	//     conflict-free (limb j of thread x at sh[j * 128 + x]), like the chain operands of k_scale / k_horner: the rolled
 	//     product loop indexes its row operand dynamically, and thread-local records of 75 k resident threads overflow L1;
 	//   * one copy of the product code serves the first term (a plain rounded product) and the fused multiply-adds.
-	constexpr int QB_SERIES_THREADS = 256;
+// One CTA of 384 threads per SM (<= 170 registers): measured best of 128 x 3, 192 x 2, 256 x 1, 256 x 2, 320 x 1, 384 x 1,
+	// 448 x 1, 512 x 1 -- the CTA is the lockstep group, so one large CTA shares instruction fetches best, and 128-register
+	// variants spill 3.4 KB per thread (profiles/r2_summary.md)
+#ifndef QB_SERIES_T
+#define QB_SERIES_T 384
+#endif
+	constexpr int QB_SERIES_THREADS = QB_SERIES_T;
 	template <int L>
 	constexpr size_t series_smem_bytes()
 	{
@@ -73,8 +79,11 @@ namespace qb
 #pragma unroll
 		for (int j = 0; j < L; ++j) v.m[j] = my[j * QB_SERIES_THREADS];
 	}
+#ifndef QB_SERIES_CTAS
+#define QB_SERIES_CTAS 1
+#endif
 	template <int L>
-	__global__ void __launch_bounds__(QB_SERIES_THREADS, 512 / QB_SERIES_THREADS)
+	__global__ void __launch_bounds__(QB_SERIES_THREADS, QB_SERIES_CTAS)
 	    k_series(DevCtx cx, int n_jobs, const mpf<L>* __restrict__ delta, const uint32_t* __restrict__ spin, const mpf<L>* __restrict__ b0,
 	             const mpf<L>* __restrict__ coef, mpf<L>* __restrict__ b)
 	{
@@ -128,9 +137,12 @@ namespace qb
 					QB_ROLL
 					for (int d = deg - 1; d >= 0; --d)
 					{
-						fast::mul_small(p, p, int64_t(n), prec);
 						ldg_rec64(cd, &c[ip * st + d]);
-						fast::add(p, p, cd, prec);
+						if ((p.sk & 3u) != K_REG || (cd.sk & 3u) != K_REG || !fast::horner_step(p, n, cd, prec))
+						{
+							fast::mul_small(p, p, int64_t(n), prec);
+							fast::add(p, p, cd, prec);
+						}
 					}
 				}
 				if (divisor)
@@ -169,11 +181,11 @@ namespace qb
 					// special values, deep cancellation: the generic routines (same correctly rounded result)
 					mpf<L> sum, r;
 					if (i == 1)
-						mul(r, p, bp, prec);
+						fast::cold_mul(r, p, bp, prec);
 					else
 					{
 						series_load(sum, mys, ssk, sexp);
-						fma(r, p, bp, sum, prec);
+						fast::cold_fma(r, p, bp, sum, prec);
 					}
 					series_store(mys, ssk, sexp, r);
 				}

@@ -112,7 +112,7 @@ namespace qb
 				mpf<L> u, v;
 				copy(u, b[size_t(tr.job0) * n1 + n]);
 				copy(v, b[size_t(tr.job1) * n1 + n]);
-				add(u, u, v, prec);
+				fast::add(u, u, v, prec);
 				mul_2si(u, u, -1);
 				fast::mul(cur, u, pt[0], prec);
 			}
@@ -133,7 +133,7 @@ namespace qb
 			{
 				mpf<L> cur;
 				chain_load(cur, my, csk, cexp);
-				mul(nxt, cur, f, prec);
+				fast::cold_mul(nxt, cur, f, prec);
 			}
 			store_rec(&at[size_t(k) * n1], nxt);
 			chain_store(my, csk, cexp, nxt);
@@ -175,7 +175,7 @@ namespace qb
 			{
 				mpf<L> s;
 				chain_load(s, my, ssk, sexp);
-				fma(r, s, rho, c, prec);
+				fast::cold_fma(r, s, rho, c, prec);
 			}
 			chain_store(my, ssk, sexp, r);
 		}

@@ -50,7 +50,7 @@ namespace qb
 
 	constexpr int QB_OFFDIAG_THREADS = 256;
 	template <int L>
-	__global__ void __launch_bounds__(QB_OFFDIAG_THREADS) k_offdiag_val(DevCtx cx, int n_tables, int n, const mpf<L>* __restrict__ S,
+	__global__ void __launch_bounds__(QB_OFFDIAG_THREADS, 2) k_offdiag_val(DevCtx cx, int n_tables, int n, const mpf<L>* __restrict__ S,
 	                                                                    const mpf<L>* __restrict__ P, const mpf<L>* __restrict__ qc, mpf<L>* g)
 	{
 		const int lambda = int(cx.lambda), dimM = cf_dim(lambda), cnt = lambda - 2 * n + 1;

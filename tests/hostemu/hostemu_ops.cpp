@@ -56,6 +56,16 @@ namespace
 			case 44: qb::fast::mul_small(r, x, p, prec); break;
 			case 45: qb::fast::add_small(r, x, p, prec); break;
 			case 46: qb::fast::div(r, x, y, prec); break;
+			case 47:  // one Horner step with an integer argument: RN(RN(x * p) + y)
+				qb::copy(r, x);
+				if ((x.sk & 3u) != qb::K_REG || (y.sk & 3u) != qb::K_REG || p <= 0 || (p >> 32) != 0 ||
+				    !qb::fast::horner_step(r, uint32_t(p), y, prec))
+				{
+					qb::fast::mul_small(r, x, p, prec);
+					qb::fast::add(r, r, y, prec);
+					r.sk |= 0x100u;  // marks "fast path declined" for the test's statistics (cleared by the harness)
+				}
+				break;
 			case 13:  // pow(x, y) with x > 0 given ln(x) in consts (extended precision)
 			case 14:  // ui_pow
 			case 15:  // exp

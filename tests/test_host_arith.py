@@ -291,3 +291,63 @@ def test_ziv_window_flags_exactly_the_values_next_to_a_midpoint(hostemu, ref):
         # whatever the window says, the value itself is MPFR's
         assert np.array_equal(out[0], ref.op("pow", prec, a=rho, b=yr)[0])
     assert flagged == truth and 5 <= flagged <= 40
+
+
+@pytest.mark.parametrize("prec", [64, 100, 600, 800, 1000, 1024, 1200, 1536])
+def test_fused_horner_step_vs_mpfr(hostemu, ref, prec):
+    """fast::horner_step -- s <- RN(RN(s n) + c), the step of the reference's Polynomial::eval with an integer argument -- against
+    mpfr_mul_ui followed by mpfr_add, on operands built to hit its corners: products whose dropped bits are exactly a tie
+    or one off a tie, all-ones mantissas (the rounding carry runs through every limb), addends that cancel the product to
+    every depth, exponent gaps around 0, 32, 64 and prec in both directions, n = 1 and n close to 2^32."""
+    from tests.golden.make_golden import rnd_num
+
+    rng = random.Random(prec * 7 + 1)
+    L = (prec + 31) // 32
+    drop = 32 * L - prec
+    S, Nn, Cc = [], [], []
+    ns = [1, 2, 3, 5, 7, 8, 100, 255, 256, 399, 400, 401, 65535, 65536, 2**31 - 1, 2**31, 2**32 - 1]
+    for it in range(700):
+        n = rng.choice(ns) if it % 3 else rng.randint(1, 400)
+        style = it % 7
+        if style == 0:      # mantissa chosen so that m * n has its dropped bits at / around the tie
+            k = n.bit_length()  # up to k bits are dropped
+            m = (rng.getrandbits(prec) | (1 << (prec - 1)))
+            target_low = rng.choice([1 << (k - 1), (1 << (k - 1)) + 1, (1 << (k - 1)) - 1, 0, (1 << k) - 1]) if k else 0
+            if n % 2 == 1 and k:
+                inv = pow(n, -1, 1 << k)
+                m = (m & ~((1 << k) - 1)) | ((target_low * inv) % (1 << k))
+            m |= 1 << (prec - 1)
+        elif style == 1:    # all ones: the rounding carry propagates to the top
+            m = (1 << prec) - 1
+            if rng.random() < 0.5:
+                m ^= rng.getrandbits(4)
+        else:
+            m = rng.getrandbits(prec) | (1 << (prec - 1))
+        e = rng.randint(-6, 12)
+        s = ref.from_int_exp(rng.getrandbits(1), m, e - prec, prec)
+        S.append(s)
+        Nn.append(n)
+        Cc.append(rnd_num(rng, prec, -6, 24))
+    S, Cc = np.stack(S), np.stack(Cc)
+    Nn = np.array(Nn, dtype=np.int64)
+    prod = ref.op("mul_si", prec, a=S, ia=Nn)
+    gaps = [0, 0, 0, 1, -1, 2, 31, 32, 33, 63, 64, 65, -31, -32, -33, -63, -64, -65, prec - 1, prec, prec + 1, prec + 70, -prec, -prec - 1, -prec - 70]
+    for i in range(0, len(S), 2):   # addends that cancel the product: -product with one bit flipped, at every exponent gap
+        if (prod[i, 0] & 3) != 1:
+            continue
+        Cc[i] = prod[i].copy()
+        Cc[i, 0] ^= 0x80000000
+        if rng.random() < 0.8:
+            li = rng.randrange(L)
+            Cc[i, 2 + li] ^= 1 << rng.randrange(31 if li == L - 1 else 32)
+        Cc[i, 2] &= (0xFFFFFFFF << drop) & 0xFFFFFFFF
+        Cc[i, 1] = np.uint32((int(np.int32(Cc[i, 1])) + rng.choice(gaps)) & 0xFFFFFFFF)
+    want = ref.op("add", prec, a=prod, b=Cc)
+    W = words(prec)
+    out = np.zeros((len(S), W), dtype=np.uint32)
+    assert hostemu.qbh_op(prec, 47, len(S), P(S), P(Cc), None, P(Nn), None, P(out), None) == 0
+    declined = int(((out[:, 0] & 0x100) != 0).sum())
+    out[:, 0] &= ~np.uint32(0x100)
+    bad = [i for i in range(len(S)) if not np.array_equal(want[i], out[i])]
+    assert not bad, (bad[:5], [int(Nn[i]) for i in bad[:5]])
+    assert declined < len(S) // 2   # the fast path takes the bulk (zeros, deep cancellations and the like fall back)
