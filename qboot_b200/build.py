@@ -17,8 +17,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
-BUILD = os.path.join(ROOT, "build", "qb")
-LIB = os.path.join(HERE, "libqboot_b200.so")
+# QB_BUILD_DIR / QB_LIB_OUT: development builds of a variant next to the in-tree library (the facade is then not relinked)
+BUILD = os.environ.get("QB_BUILD_DIR") or os.path.join(ROOT, "build", "qb")
+LIB = os.environ.get("QB_LIB_OUT") or os.path.join(HERE, "libqboot_b200.so")
 # the C++ facade (include/qboot/*.hpp + qboot_b200/host/*.cpp): plain host C++17, reaches CUDA only through the C ABI above
 FACADE = os.path.join(HERE, "libqboot.so")
 HOST = os.path.join(HERE, "host")
@@ -95,7 +96,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
         _run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "shared"], os.path.join(BUILD, "link.log"))
         if verbose:
             print(f"built {LIB} ({len(todo)} objects compiled)")
-    build_facade(force=force, verbose=verbose)
+    if not os.environ.get("QB_LIB_OUT"):
+        build_facade(force=force, verbose=verbose)
     return LIB
 
 

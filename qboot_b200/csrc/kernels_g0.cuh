@@ -34,7 +34,7 @@ namespace qb
 		const int K = sp == 0 ? 6 : 8, deg = sp == 0 ? 3 : 4, st = deg + 1;
 		if (c >= K * st) return;
 		int i = c / st, d = c % st;
-		mpf<L>* out = coef + size_t(job) * QB_NCOEF;
+		uint32_t* out = reinterpret_cast<uint32_t*>(coef);
 		const HorPoly* polys = sp == 0 ? QB_HOR_POLY_0 : QB_HOR_POLY_1;
 		const HorMono* monos = sp == 0 ? QB_HOR_MONO_0 : QB_HOR_MONO_1;
 		mpf<L> lD, lS, lP;
@@ -45,14 +45,14 @@ namespace qb
 			copy(lS, S[job]);
 			copy(lP, P[job]);
 			hor_coefficient(r, polys[(i - 1) * st + d], monos, lD, lS, lP, sp, cx.eps, cx.prec);
-			copy(out[c], r);
+			coef_store(out, c, job, n_jobs, r);
 			return;
 		}
 		// p_0 and p_{K-1}: products of linear factors; the d == 0 thread of each builds the whole polynomial
 		if (d != 0) return;
 		mpf<L> pe[5];
 		rec_coeffs_end(pe, lD, sp, cx.eps, cx.prec, i == 0);
-		for (int k = 0; k < st; ++k) copy(out[i * st + k], pe[k]);
+		for (int k = 0; k < st; ++k) coef_store(out, i * st + k, job, n_jobs, pe[k]);
 	}
 
 	// Elementwise primitive (diagnostic entry qb_op_batch): lets the GPU test-suite pin the device build of every

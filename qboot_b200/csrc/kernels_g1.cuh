@@ -114,7 +114,8 @@ namespace qb
 		// keep ONE copy of the loop bodies below (no per-spin clones: the kernel must stay inside the instruction cache)
 		asm volatile("" : "+r"(K), "+r"(deg));
 		const int st = deg + 1;
-		const mpf<L>* c = coef + size_t(active ? job : 0) * QB_NCOEF;
+		const uint32_t* cw = reinterpret_cast<const uint32_t*>(coef);  // word-planar across the jobs of this launch (launch.cuh)
+		const int cj = active ? job : 0;
 		uint32_t psk, ssk = K_ZERO;
 		int32_t pexp, sexp = 0;
 		for (uint32_t n = 1; n <= n_max; ++n)
@@ -133,11 +134,11 @@ namespace qb
 				mpf<L> p;
 				{
 					mpf<L> cd;
-					ldg_rec64(p, &c[ip * st + deg]);
+					coef_load(p, cw, ip * st + deg, cj, n_jobs);
 					QB_ROLL
 					for (int d = deg - 1; d >= 0; --d)
 					{
-						ldg_rec64(cd, &c[ip * st + d]);
+						coef_load(cd, cw, ip * st + d, cj, n_jobs);
 						if ((p.sk & 3u) != K_REG || (cd.sk & 3u) != K_REG || !fast::horner_step(p, n, cd, prec))
 						{
 							fast::mul_small(p, p, int64_t(n), prec);

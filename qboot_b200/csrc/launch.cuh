@@ -45,6 +45,26 @@ namespace qb
 	};
 
 	constexpr int QB_NCOEF = 40;  // 8 polynomials x 5 coefficients (spin 0 uses 6 x 4 of them)
+	// The recurrence coefficients of one launch (n_jobs series jobs) are stored WORD-PLANAR across jobs: word w of
+	// coefficient c of job j at base[(c * W + w) * n_jobs + j].  Writer (k_rec_coeffs) and reader (k_series) both run with
+	// the job as the lane index, so every access of a warp is one contiguous 128-byte line (the record-per-job layout cost
+	// 32 sectors per 8-byte load and is read 400 times per job).
+	template <int L>
+	QB_HD QB_INLINE void coef_store(uint32_t* base, int c, int job, int n_jobs, const mpf<L>& v)
+	{
+		uint32_t* p = base + size_t(c) * (L + 2) * size_t(n_jobs) + job;
+		p[0] = v.sk;
+		p[size_t(n_jobs)] = uint32_t(v.exp);
+		for (int j = 0; j < L; ++j) p[size_t(2 + j) * size_t(n_jobs)] = v.m[j];
+	}
+	template <int L>
+	QB_HD QB_INLINE void coef_load(mpf<L>& v, const uint32_t* base, int c, int job, int n_jobs)
+	{
+		const uint32_t* p = base + size_t(c) * (L + 2) * size_t(n_jobs) + job;
+		v.sk = p[0];
+		v.exp = int32_t(p[size_t(n_jobs)]);
+		for (int j = 0; j < L; ++j) v.m[j] = p[size_t(2 + j) * size_t(n_jobs)];
+	}
 
 	template <int L>
 	void launch_rec_coeffs(const DevCtx& cx, int n_jobs, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* S,
