@@ -14,6 +14,7 @@
 #include <cassert>
 #include <cstdint>
 #include <memory>
+#include <array>
 #include <optional>
 #include <utility>
 #include <vector>
@@ -47,6 +48,9 @@ namespace qboot
 		mutable algebra::Vector<algebra::Vector<algebra::Matrix<mp::real>>> mat_;
 		algebra::Vector<algebra::Matrix<mp::real>> target_{};
 		b200::DeviceBlock dev_{};
+		// bilinear bases at the sample points when convert has already evaluated them (underneath its GPU phase)
+		std::optional<std::array<algebra::Matrix<mp::real>, 2>> bilinear_{};
+		friend class BootstrapEquation;
 		void fetch() const;  // device -> mat_
 		[[nodiscard]] algebra::Matrix<algebra::Polynomial> as_polynomial(algebra::Vector<algebra::Matrix<mp::real>>&& vals);
 		friend class PolynomialProgram;

@@ -149,6 +149,7 @@ namespace qb
 		DevBuf d_ziv;  // two counters of the powers' Ziv loop
 		int ziv_slack = QB_ZIV_SLACK;
 		uint64_t ziv_reported = 0;
+		DevBuf d_coefx;  // fixed-point copy of the recurrence coefficients (polyfx.cuh)
 		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_qc, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms, d_fb_g;
 		DevCtx cx{};
 		int n_tables = 0, n_jobs = 0;
@@ -180,7 +181,7 @@ namespace qb
 		~Engine() override
 		{
 			cudaSetDevice(device);
-			for (DevBuf* b : {&d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_qc, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
+			for (DevBuf* b : {&d_ziv, &d_coefx, &d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_qc, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
 			                  &d_fb_terms, &d_fb_g})
 				b->release();
 			pmp_release();
@@ -494,6 +495,7 @@ namespace qb
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
+			    d_coefx.ensure(4 * size_t(fx_words<L>()) * QB_NCOEF * nj) ||
 			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (2 * n1 + 1) * nt) || d_qc.ensure(sizeof(T) * nt) || d_a.ensure(sizeof(T) * a_slot_records) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;
@@ -535,12 +537,14 @@ namespace qb
 		{
 			launch_rec_coeffs<L>(cx, r.j1 - r.j0, j_delta + r.j0, j_spin + r.j0, j_S + r.j0, j_P + r.j0,
 			                     d_coef.as<T>() + size_t(r.j0) * QB_NCOEF, st);
-			++launches;
+			launch_coef_fx<L>(cx, r.j1 - r.j0, j_spin + r.j0, d_coef.as<T>() + size_t(r.j0) * QB_NCOEF,
+			                  d_coefx.as<uint32_t>() + size_t(r.j0) * QB_NCOEF * fx_words<L>(), st);
+			launches += 2;
 		}
 		void stage_series(const Range& r, cudaStream_t st)
 		{
 			launch_series<L>(cx, r.j1 - r.j0, j_delta + r.j0, j_spin + r.j0, j_b0 + r.j0, d_coef.as<T>() + size_t(r.j0) * QB_NCOEF,
-			                 d_b.as<T>() + size_t(r.j0) * (size_t(n_max) + 1), st);
+			                 d_coefx.as<uint32_t>() + size_t(r.j0) * QB_NCOEF * fx_words<L>(), d_b.as<T>() + size_t(r.j0) * (size_t(n_max) + 1), st);
 			++launches;
 		}
 		void stage_pow(const Range& r, cudaStream_t st)

@@ -28,9 +28,9 @@ namespace qb
 		// (measured: 96 local loads / stores per mul_small, 130 + 154 per fma, 13 % of all instructions of k_series).  The
 		// fall-backs therefore work on copies made inside the cold branch; the caller's records stay in registers.
 		// QB_COLD_COPY = 0 hands the caller's records over directly.  Which is faster is decided per kernel group by measurement
-		// (kernel_inst.cu): the copies win where registers are plentiful (k_series at 170 registers: -19 %), and lose in the
-		// 128-register kernels (k_scale / k_horner +4 %, transverse recursion +11 %, coefficients +21 %), whose operands are
-		// better off in L1-resident local memory than competing for registers.
+		// (kernel_inst.cu): the copies win in k_series (170 registers: -19 %) and k_scale (-2 %), and lose in k_horner (+6 %),
+		// the transverse recursion (+11 %) and the coefficients (+21 %), whose operands are better off in L1-resident local
+		// memory than competing for registers (profiles/r2_summary.md).
 #ifndef QB_COLD_COPY
 #define QB_COLD_COPY 0
 #endif

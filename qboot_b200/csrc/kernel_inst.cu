@@ -1,18 +1,19 @@
-// qboot_b200 -- kernel translation unit: nvcc -DQB_L=<limbs> -DQB_KGROUP=<0..4> kernel_inst.cu
+// qboot_b200 -- kernel translation unit: nvcc -DQB_L=<limbs> -DQB_KGROUP=<0..6> kernel_inst.cu
 //   group 0: k_rec_coeffs, k_ops    1: k_series    2: k_scale, k_horner    3: k_rho_to_z, k_offdiag_val, k_offdiag_close    4: k_vtod, k_fblock, k_pow
+//   group 6: k_horner (its own unit so that k_scale and k_horner can differ in QB_COLD_COPY)
 //   group 5: k_pmp_accum, k_pmp_pack, k_dec_format, k_dec_gather (the last one is not templated: compiled once, -DQB_L_FIRST=<smallest L>)
 #if !defined(QB_L) || !defined(QB_KGROUP)
-#error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..5>"
+#error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..6>"
 #endif
 #include <cstdlib>
-#if QB_KGROUP == 1 && !defined(QB_COLD_COPY)
-#define QB_COLD_COPY 1  // see fastops.cuh, "cold paths"
+#if (QB_KGROUP == 1 || QB_KGROUP == 2) && !defined(QB_COLD_COPY)
+#define QB_COLD_COPY 1  // see fastops.cuh, "cold paths": measured per group -- on for k_series (-19 %) and k_scale (-2 %), off elsewhere
 #endif
 #if QB_KGROUP == 0
 #include "kernels_g0.cuh"
 #elif QB_KGROUP == 1
 #include "kernels_g1.cuh"
-#elif QB_KGROUP == 2
+#elif QB_KGROUP == 2 || QB_KGROUP == 6
 #include "kernels_g2.cuh"
 #elif QB_KGROUP == 3
 #include "kernels_g3.cuh"
@@ -40,15 +41,23 @@ namespace qb
 	}
 #elif QB_KGROUP == 1
 	template <>
+	void launch_coef_fx<QB_L>(const DevCtx& cx, int n_jobs, const uint32_t* spin, const mpf<QB_L>* coef, uint32_t* coefx, cudaStream_t st)
+	{
+		const int threads = 128;
+		const int64_t total = int64_t(n_jobs) * 8;
+		k_coef_fx<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_jobs, spin, coef, coefx);
+	}
+	template <>
 	void launch_series<QB_L>(const DevCtx& cx, int n_jobs, const mpf<QB_L>* delta, const uint32_t* spin, const mpf<QB_L>* b0,
-	                         const mpf<QB_L>* coef, mpf<QB_L>* b, cudaStream_t st)
+	                         const mpf<QB_L>* coef, const uint32_t* coefx, mpf<QB_L>* b, cudaStream_t st)
 	{
 		static const bool attr_set = [] {
 			cudaFuncSetAttribute(k_series<QB_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(series_smem_bytes<QB_L>()));
 			return true;
 		}();
 		(void)attr_set;
-		k_series<QB_L><<<(n_jobs + QB_SERIES_THREADS - 1) / QB_SERIES_THREADS, QB_SERIES_THREADS, series_smem_bytes<QB_L>(), st>>>(cx, n_jobs, delta, spin, b0, coef, b);
+		k_series<QB_L><<<(n_jobs + QB_SERIES_THREADS - 1) / QB_SERIES_THREADS, QB_SERIES_THREADS, series_smem_bytes<QB_L>(), st>>>(cx, n_jobs, delta, spin, b0,
+		                                                                                                                      coef, coefx, b);
 	}
 #elif QB_KGROUP == 2
 	template <>
@@ -58,14 +67,6 @@ namespace qb
 		int threads = QB_DERIV_THREADS;
 		int64_t total = int64_t(n_tables) * (cx.n_max + 1);
 		k_scale<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, tref, b, pw, a);
-	}
-	template <>
-	void launch_horner<QB_L>(const DevCtx& cx, int n_tables, const mpf<QB_L>* a, const mpf<QB_L>* pw, mpf<QB_L>* fr,
-	                         cudaStream_t st)
-	{
-		int threads = QB_DERIV_THREADS;
-		int64_t total = int64_t(n_tables) * (int(cx.lambda) + 1);
-		k_horner<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, a, pw, fr);
 	}
 #elif QB_KGROUP == 3
 	template <>
@@ -140,6 +141,15 @@ namespace qb
 		k_dec_gather<<<unsigned((n * 32 + threads - 1) / threads), threads, 0, st>>>(n, slots, slot, len, ofs, text);
 	}
 #endif
+#elif QB_KGROUP == 6
+	template <>
+	void launch_horner<QB_L>(const DevCtx& cx, int n_tables, const mpf<QB_L>* a, const mpf<QB_L>* pw, mpf<QB_L>* fr,
+	                         cudaStream_t st)
+	{
+		int threads = QB_DERIV_THREADS;
+		int64_t total = int64_t(n_tables) * (int(cx.lambda) + 1);
+		k_horner<QB_L><<<unsigned((total + threads - 1) / threads), threads, 0, st>>>(cx, n_tables, a, pw, fr);
+	}
 #else
 #error "QB_KGROUP out of range"
 #endif

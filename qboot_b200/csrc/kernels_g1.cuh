@@ -16,6 +16,7 @@
 #define QB_TABLE_QUAL static __device__
 #include "block.cuh"
 #include "launch.cuh"
+#include "polyfx.cuh"
 
 namespace qb
 {
@@ -38,6 +39,46 @@ namespace qb
 		}
 		else
 			copy(d, *src);
+	}
+
+	// Fixed-point frames of the recurrence polynomials (polyfx.cuh): one thread per (polynomial, job), job fastest.  Chooses
+	// the frame exponent from the coefficients' exponents and n_max, converts every coefficient and records whether all of
+	// them are exact in the frame; k_series evaluates such polynomials on integers and the others in floating point.
+	template <int L>
+	__global__ void k_coef_fx(DevCtx cx, int n_jobs, const uint32_t* __restrict__ spin, const mpf<L>* __restrict__ coef,
+	                          uint32_t* __restrict__ coefx)
+	{
+		constexpr int W = L + 2, FW = fx_words<L>();
+		const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+		const int i = gid / n_jobs, job = gid - i * n_jobs;
+		if (i >= 8) return;
+		const int K = spin[job] == 0 ? 6 : 8, deg = spin[job] == 0 ? 3 : 4, st = deg + 1;
+		if (i >= K) return;
+		const uint32_t* cw = reinterpret_cast<const uint32_t*>(coef);
+		int32_t e[5];
+		bool have[5];
+		for (int d = 0; d <= deg; ++d)
+		{
+			const uint32_t* p = cw + size_t(i * st + d) * W * size_t(n_jobs) + job;
+			have[d] = (p[0] & 3u) == K_REG;
+			e[d] = int32_t(p[size_t(n_jobs)]);
+		}
+		const int nbits = 32 - clz32(cx.n_max);
+		const int32_t E = fx::frame_exponent(e, have, deg, nbits);
+		bool ok = true;
+		for (int d = 0; d <= deg; ++d)
+		{
+			mpf<L> c;
+			coef_load(c, cw, i * st + d, job, n_jobs);
+			uint32_t V[W], sg;
+			ok = fx::from_record<L>(V, sg, c, E) && ok;
+			uint32_t* q = coefx + size_t(i * st + d) * FW * size_t(n_jobs) + job;
+			q[0] = sg;
+			q[size_t(n_jobs)] = uint32_t(E);
+			for (int j = 0; j < W; ++j) q[size_t(2 + j) * size_t(n_jobs)] = V[j];
+		}
+		// the verdict goes into the leading coefficient's header
+		coefx[size_t(i * st + deg) * FW * size_t(n_jobs) + job] |= ok ? 1u : 0u;
 	}
 
 	// The series recurrence b[n] = -(sum_{i=1}^{min(n,K-1)} p_i(n) b[n-i]) / p_0(n)       (src/hor_recursion.cpp:31-37),
@@ -85,7 +126,7 @@ namespace qb
 	template <int L>
 	__global__ void __launch_bounds__(QB_SERIES_THREADS, QB_SERIES_CTAS)
 	    k_series(DevCtx cx, int n_jobs, const mpf<L>* __restrict__ delta, const uint32_t* __restrict__ spin, const mpf<L>* __restrict__ b0,
-	             const mpf<L>* __restrict__ coef, mpf<L>* __restrict__ b)
+	             const mpf<L>* __restrict__ coef, const uint32_t* __restrict__ coefx, mpf<L>* __restrict__ b)
 	{
 		extern __shared__ uint32_t sh[];
 		uint32_t* myp = sh + threadIdx.x;                           // p_i(n)
@@ -132,6 +173,55 @@ namespace qb
 				if (!active || (!divisor && (i >= K || uint32_t(i) > n))) continue;
 				const int ip = divisor ? 0 : i;
 				mpf<L> p;
+				// the polynomial in its fixed-point frame (polyfx.cuh) when its coefficients are exact there ...
+				bool fixed = false;
+				{
+					constexpr int W = L + 2, FW = fx_words<L>();
+					const size_t cstride = size_t(FW) * size_t(n_jobs);
+					// The coefficients (5.8 KB per job) stream from DRAM at every step -- the jobs in flight hold 300 MB of
+					// them.  Each lane touches one line of the NEXT polynomial's coefficients now, a polynomial ahead of their use
+					// (the lanes of a warp read the same lines: word-planar layout), so that the loads below find them in L2.
+					{
+						const int ipn = divisor ? 1 : (i + 1 < K ? i + 1 : 0);
+						const uint32_t* nb = coefx + size_t(ipn * st) * cstride + (cj & ~31);
+						QB_ROLL
+						for (int idx = int(threadIdx.x & 31u); idx < st * FW; idx += 32)
+							asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + size_t(idx) * size_t(n_jobs)));
+					}
+					const uint32_t* q = coefx + size_t(ip * st + deg) * cstride + cj;
+					uint32_t sg = q[0];
+					if (sg & 1u)
+					{
+						const int32_t E = int32_t(q[size_t(n_jobs)]);
+						uint32_t V[W], C[W], Cn[W], csgn;
+#pragma unroll
+						for (int j = 0; j < W; ++j) V[j] = q[size_t(2 + j) * size_t(n_jobs)];
+						// software pipeline: the coefficient of the next Horner step is in flight while this one is computed
+						q -= cstride;
+						csgn = q[0];
+#pragma unroll
+						for (int j = 0; j < W; ++j) Cn[j] = q[size_t(2 + j) * size_t(n_jobs)];
+						fixed = true;
+						QB_ROLL
+						for (int d = deg - 1; d >= 0; --d)
+						{
+							const uint32_t csg = csgn;
+#pragma unroll
+							for (int j = 0; j < W; ++j) C[j] = Cn[j];
+							if (d > 0)
+							{
+								q -= cstride;
+								csgn = q[0];
+#pragma unroll
+								for (int j = 0; j < W; ++j) Cn[j] = q[size_t(2 + j) * size_t(n_jobs)];
+							}
+							if (fixed) fixed = fx::horner_step<L>(V, sg, n, C, csg, prec);
+						}
+						if (fixed) fixed = fx::to_record<L>(p, V, sg, E);
+					}
+				}
+				// ... and in floating point otherwise (frame not exact, a deep cancellation, a zero)
+				if (!fixed)
 				{
 					mpf<L> cd;
 					coef_load(p, cw, ip * st + deg, cj, n_jobs);

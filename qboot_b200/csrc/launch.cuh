@@ -69,9 +69,19 @@ namespace qb
 	template <int L>
 	void launch_rec_coeffs(const DevCtx& cx, int n_jobs, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* S,
 	                       const mpf<L>* P, mpf<L>* coef, cudaStream_t st);
+	// Fixed-point copy of the coefficients (polyfx.cuh), word-planar like `coef`: QB_FX_WORDS words per coefficient --
+	// [0] sign | 1 if the whole polynomial is exact in its frame (meaningful in the leading coefficient), [1] frame exponent,
+	// [2 .. 2 + L + 2) the magnitude in the frame.
+	template <int L>
+	QB_HD constexpr int fx_words()
+	{
+		return L + 4;
+	}
+	template <int L>
+	void launch_coef_fx(const DevCtx& cx, int n_jobs, const uint32_t* spin, const mpf<L>* coef, uint32_t* coefx, cudaStream_t st);
 	template <int L>
 	void launch_series(const DevCtx& cx, int n_jobs, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* b0,
-	                   const mpf<L>* coef, mpf<L>* b, cudaStream_t st);
+	                   const mpf<L>* coef, const uint32_t* coefx, mpf<L>* b, cudaStream_t st);
 	template <int L>
 	void launch_scale(const DevCtx& cx, int n_tables, const TableRef* tref, const mpf<L>* b, const mpf<L>* pw, mpf<L>* a,
 	                  cudaStream_t st);

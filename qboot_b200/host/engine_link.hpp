@@ -41,6 +41,7 @@ namespace qboot::b200
 		// text of all constraints as produced by qb_pmp_text (pinned host memory), and where each piece starts
 		char* text = nullptr;
 		int64_t text_bytes = 0;
+		size_t text_cap = 0;  // bytes of the pinned buffer behind `text`
 		std::vector<int64_t> sizes, offsets;  // 2 per block: d_B text, d_c text
 		int text_digits = 0;
 		std::mutex mu;
@@ -61,6 +62,10 @@ namespace qboot::b200
 		Pinned(const Pinned&) = delete;
 		Pinned& operator=(const Pinned&) = delete;
 	};
+	// Page-locking hundreds of megabytes costs more than filling them (~0.1 s for the 400 MB of text of a mixed-correlator
+	// program), so the process keeps the largest released buffer for the next taker.
+	char* pinned_acquire(size_t bytes, size_t& capacity);
+	void pinned_release(char* p, size_t bytes);
 	// n numbers (records, host) -> their SDPB text lines, formatted on the device (qb_dec_format) with the host formatter
 	// for the few the device declines; appended to `out`
 	void format_numbers(Engine& e, int ndigits, const uint32_t* recs, size_t n, std::string& out);

@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "engine_link.hpp"
+#include <mutex>
+
 #include "qboot/context.hpp"
 #include "qboot/primary_op.hpp"
 #include "qboot/task_queue.hpp"
@@ -68,7 +70,48 @@ namespace qboot
 			if (!p && bytes) throw std::bad_alloc();
 		}
 		Pinned::~Pinned() { qb_pinned_free(p); }
-		PackedProgram::~PackedProgram() { qb_pinned_free(text); }
+		PackedProgram::~PackedProgram() { pinned_release(text, text_cap); }
+		namespace
+		{
+			std::mutex pinned_mu;
+			char* pinned_spare = nullptr;
+			size_t pinned_spare_bytes = 0;
+		}  // namespace
+		char* pinned_acquire(size_t bytes, size_t& capacity)
+		{
+			capacity = 0;
+			if (bytes == 0) return nullptr;
+			{
+				std::lock_guard<std::mutex> g(pinned_mu);
+				if (pinned_spare && pinned_spare_bytes >= bytes)
+				{
+					char* p = pinned_spare;
+					capacity = pinned_spare_bytes;
+					pinned_spare = nullptr;
+					pinned_spare_bytes = 0;
+					return p;
+				}
+			}
+			char* p = static_cast<char*>(qb_pinned_alloc(bytes));
+			if (!p) throw std::bad_alloc();
+			capacity = bytes;
+			return p;
+		}
+		void pinned_release(char* p, size_t bytes)
+		{
+			if (!p) return;
+			char* drop = p;
+			{
+				std::lock_guard<std::mutex> g(pinned_mu);
+				if (bytes > pinned_spare_bytes)
+				{
+					drop = pinned_spare;
+					pinned_spare = p;
+					pinned_spare_bytes = bytes;
+				}
+			}
+			qb_pinned_free(drop);
+		}
 		void format_numbers(Engine& e, int ndigits, const uint32_t* recs, size_t n, std::string& out)
 		{
 			if (n == 0) return;

@@ -17,6 +17,7 @@
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <thread>
 #include <unordered_map>
 
 #include "engine_link.hpp"
@@ -137,6 +138,7 @@ namespace qboot
 			int32_t op_index;                      // -1: discrete sector
 			unique_ptr<ConformalScale> scale;      // continuous only
 			Vector<real> deltas;                   // sample Deltas (continuous only)
+			std::optional<std::array<Matrix<real>, 2>> bilinear{};  // q_m(x_k) sqrt(s_k [x_k]), computed while the GPU works
 		};
 		const BootstrapEquation& be;
 		std::shared_ptr<b200::Engine> engine;
@@ -326,6 +328,7 @@ namespace qboot
 	{
 		throw std::logic_error("qboot_b200: get_spectrum (extremal functional method) is outside the scope of this engine");
 	}
+	static std::array<Matrix<real>, 2> bilinear_at_samples(const ScaleFactor& chi);
 	// src/bootstrap_equation.cpp:555-593, batched
 	PolynomialProgram BootstrapEquation::convert(const unique_ptr<SDPMode>& mode, uint32_t parallel, const unique_ptr<_event_base>& event) const
 	{
@@ -360,8 +363,39 @@ namespace qboot
 		}
 		plan.build_terms();
 		{
-			_scoped_event scope("tables + assembly (GPU)", event);
-			plan.run();
+			// The GPU computes the tables and assembles the constraint blocks while the host threads evaluate the bilinear bases
+			// at the sample points (create_input's other half: independent of the tables, src/polynomial_program.cpp:224-229).
+			_scoped_event scope("tables + assembly (GPU) | bilinear bases (host)", event);
+			std::exception_ptr gpu_error;
+			std::thread gpu([&] {
+				try
+				{
+					_scoped_event inner("tables + assembly (GPU)", event);
+					plan.run();
+				}
+				catch (...)
+				{
+					gpu_error = std::current_exception();
+				}
+			});
+			vector<std::function<int()>> tasks;
+			for (auto& it : plan.items)
+				if (it.op_index >= 0 && it.scale)
+					tasks.emplace_back([&it] {
+						it.bilinear = bilinear_at_samples(*it.scale);
+						return 0;
+					});
+			try
+			{
+				_parallel_evaluate(tasks, std::max(parallel, cont_.parallel()));
+			}
+			catch (...)
+			{
+				gpu.join();
+				throw;
+			}
+			gpu.join();
+			if (gpu_error) std::rethrow_exception(gpu_error);
 		}
 		// discrete sectors come back to the host: the mode's normalisation / objective vectors are built from them
 		disc_cache_.clear();
@@ -381,7 +415,11 @@ namespace qboot
 			auto& item = plan.items[o.item];
 			const uint32_t sz = sec.size();
 			if (item.op_index >= 0)
-				prg.add_inequality(PolynomialInequality(N_, sz, move(item.scale), b200::DeviceBlock{plan.engine, int32_t(o.item), plan.epoch}));
+			{
+				PolynomialInequality ineq(N_, sz, move(item.scale), b200::DeviceBlock{plan.engine, int32_t(o.item), plan.epoch});
+				ineq.bilinear_ = move(item.bilinear);
+				prg.add_inequality(move(ineq));
+			}
 			else if (sec.is_matrix())
 				prg.add_inequality(PolynomialInequality(N_, sz, std::make_unique<TrivialScale>(), b200::DeviceBlock{plan.engine, int32_t(o.item), plan.epoch}));
 			else
@@ -554,6 +592,23 @@ namespace qboot
 		}
 		return {move(constant), move(obj_new)};
 	}
+	// bilinear bases at the sample points (src/polynomial_program.cpp:224-229): q0[m][k] = q_m(x_k) sqrt(s_k),
+	// q1[m][k] = q_m(x_k) sqrt(s_k x_k)
+	static std::array<Matrix<real>, 2> bilinear_at_samples(const ScaleFactor& chi)
+	{
+		const uint32_t deg = chi.max_degree(), d0 = deg / 2, d1 = deg == 0 ? 0 : (deg - 1) / 2;
+		Matrix<real> q0(d0 + 1, deg + 1), q1(d1 + 1, deg + 1);
+		const auto xs = chi.sample_points();
+		const auto scs = chi.sample_scalings();
+		const auto q = chi.bilinear_bases();
+		for (uint32_t k = 0; k <= deg; ++k)
+		{
+			const real s0 = mp::sqrt(scs[k]), s1 = mp::sqrt(scs[k] * xs[k]);
+			for (uint32_t m = 0; m <= d0; ++m) q0.at(m, k) = q[m].eval(xs[k]) * s0;
+			for (uint32_t m = 0; m <= d1; ++m) q1.at(m, k) = q[m].eval(xs[k]) * s1;
+		}
+		return {move(q0), move(q1)};
+	}
 	// src/polynomial_program.cpp:152-232 -- the per-inequality loops run as ONE pack kernel over all blocks
 	SDPBInput PolynomialProgram::create_input(uint32_t parallel, const unique_ptr<_event_base>& event) &&
 	{
@@ -618,24 +673,16 @@ namespace qboot
 			eng->check(qb_pmp_pack(eng->h, int(J), sel.data(), int(eq_sz), lead.data(), int(M), free_idx.data(), eqn.data(), eqt.data()), "qb_pmp_pack");
 			packed->pack_epoch = ++eng->pack_epoch;
 		}
-		// bilinear bases at the sample points, on host threads: q0[m][k] = q_m(x_k) sqrt(s_k), q1[m][k] = q_m(x_k) sqrt(s_k x_k)
+		// bilinear bases at the sample points, on host threads
 		vector<std::function<int()>> tasks;
 		for (uint32_t j = 0; j < J; ++j)
 			tasks.emplace_back([this, &sdpb, &packed, j, M, &event] {
 				_scoped_event scope(std::to_string(j), event);
 				auto& ineq = inequality_[j].value();
-				const uint32_t sz = ineq.size(), deg = ineq.max_degree(), d0 = deg / 2, d1 = deg == 0 ? 0 : (deg - 1) / 2;
-				Matrix<real> q0(d0 + 1, deg + 1), q1(d1 + 1, deg + 1);
-				const auto xs = ineq.sample_points();
-				const auto scs = ineq.sample_scalings();
-				const auto q = ineq.bilinear_bases();
-				for (uint32_t k = 0; k <= deg; ++k)
-				{
-					const real s0 = mp::sqrt(scs[k]), s1 = mp::sqrt(scs[k] * xs[k]);
-					for (uint32_t m = 0; m <= d0; ++m) q0.at(m, k) = q[m].eval(xs[k]) * s0;
-					for (uint32_t m = 0; m <= d1; ++m) q1.at(m, k) = q[m].eval(xs[k]) * s1;
-				}
-				sdpb.register_constraint(j, DualConstraint(sz, deg, packed, int32_t(j), int32_t(M), {move(q0), move(q1)}));
+				const uint32_t sz = ineq.size(), deg = ineq.max_degree();
+				// (convert already computed them underneath the GPU phase for the constraints it built)
+				auto bl = ineq.bilinear_ ? move(*ineq.bilinear_) : bilinear_at_samples(*ineq.chi_);
+				sdpb.register_constraint(j, DualConstraint(sz, deg, packed, int32_t(j), int32_t(M), move(bl)));
 				inequality_[j].reset();
 				return 0;
 			});
@@ -724,9 +771,13 @@ namespace qboot
 			offsets.assign(sizes.size() + 1, 0);
 			for (size_t i = 0; i < sizes.size(); ++i) offsets[i + 1] = offsets[i] + sizes[i];
 			text_bytes = offsets.back();
-			qb_pinned_free(text);
-			text = text_bytes ? static_cast<char*>(qb_pinned_alloc(size_t(text_bytes))) : nullptr;
-			if (text_bytes && !text) throw std::bad_alloc();
+			if (size_t(text_bytes) > text_cap)
+			{
+				pinned_release(text, text_cap);
+				text = nullptr;
+				text_cap = 0;
+				text = pinned_acquire(size_t(text_bytes), text_cap);
+			}
 			engine->check(qb_pmp_text_fetch(engine->h, text), "qb_pmp_text_fetch");
 			text_digits = ndigits;
 		}
@@ -799,11 +850,29 @@ namespace qboot
 		std::shared_ptr<b200::PackedProgram> packed;
 		for (uint32_t j = 0; j < J; ++j)
 			if (constraints_[j]->dev_) packed = constraints_[j]->dev_;
+		// the device formats the large arrays while host threads write the small files (blocks, objectives, bilinear bases)
+		std::exception_ptr text_error;
+		std::thread text_thread;
 		if (packed)
+			text_thread = std::thread([&] {
+				try
+				{
+					_scoped_event scope("decimal text (GPU)", event);
+					packed->ensure_text(nd);
+				}
+				catch (...)
+				{
+					text_error = std::current_exception();
+				}
+			});
+		struct Joiner
 		{
-			_scoped_event scope("decimal text (GPU)", event);
-			packed->ensure_text(nd);
-		}
+			std::thread& t;
+			~Joiner()
+			{
+				if (t.joinable()) t.join();
+			}
+		} joiner{text_thread};
 		std::shared_ptr<b200::Engine> eng = packed ? packed->engine : std::make_shared<b200::Engine>(mp::_prec(), 1u, 1u, mp::rational(1, 2));
 		const size_t W = size_t(eng->words);
 		vector<std::function<int()>> tasks;
@@ -862,6 +931,10 @@ namespace qboot
 			write_file(root / "objectives", out, nullptr, 0);
 			return 0;
 		});
+		_parallel_evaluate(tasks, parallel);
+		tasks.clear();
+		if (text_thread.joinable()) text_thread.join();
+		if (text_error) std::rethrow_exception(text_error);
 		for (uint32_t i = 0; i < J; ++i)
 			tasks.emplace_back([&, i] {
 				_scoped_event scope("write constraint " + std::to_string(i), event);

@@ -9,6 +9,10 @@
 #include <chrono>
 #include <cstring>
 #include <map>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -119,6 +123,38 @@ namespace
 		return boot;
 	}
 	double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	// QBF_TRACE=1: print the duration of every named phase (the façade's _scoped_event hooks, as the reference's WatchScope does
+	// in debug builds) to stderr; per-constraint scopes (names starting with a digit or containing " in ") are summed
+	class Trace : public qboot::_event_base
+	{
+		std::mutex mu_;
+		std::map<std::string, double> t0_;
+		double small_ = 0;
+	public:
+		void on_begin(std::string_view tag) override
+		{
+			std::lock_guard<std::mutex> g(mu_);
+			t0_[std::string(tag)] = now();
+		}
+		void on_end(std::string_view tag) override
+		{
+			std::lock_guard<std::mutex> g(mu_);
+			const std::string k(tag);
+			const double dt = now() - t0_[k];
+			const bool minor = k.empty() || (k[0] >= '0' && k[0] <= '9') || k.find(" in ") != std::string::npos;
+			if (minor)
+				small_ += dt;
+			else
+				std::fprintf(stderr, "[qbf] %-32s %8.1f ms\n", k.c_str(), 1e3 * dt);
+		}
+		~Trace() override { std::fprintf(stderr, "[qbf] %-32s %8.1f ms (summed over host threads)\n", "per-constraint host tasks", 1e3 * small_); }
+	};
+	std::unique_ptr<qboot::_event_base> make_trace()
+	{
+		const char* e = std::getenv("QBF_TRACE");
+		if (e && *e && *e != '0') return std::make_unique<Trace>();
+		return {};
+	}
 	thread_local std::string last_error;
 }  // namespace
 
@@ -141,18 +177,20 @@ extern "C"
 			if (de1 && *de1) d["e1"] = qboot::mp::parse(de1).value();
 			qboot::Context c(n_max, lambda, rational(std::string_view(dim)), threads);
 			auto boot = model == 0 ? model_single(c, d, numax, maxspin, finite != 0) : model_mixed(c, d, numax, maxspin, finite != 0);
+			const auto trace = make_trace();
 			const double t0 = now();
-			auto pmp = mode == 0 ? boot.convert(qboot::FindContradiction("unit"), threads) : boot.convert(qboot::ExtremalOPE(true, "T", "unit"), threads);
+			auto pmp = mode == 0 ? boot.convert(qboot::FindContradiction("unit"), threads, trace)
+			                     : boot.convert(qboot::ExtremalOPE(true, "T", "unit"), threads, trace);
 			const double t1 = now();
 			if (counts) counts[1] = int64_t(pmp.num_of_variables());
-			auto input = std::move(pmp).create_input(threads);
+			auto input = std::move(pmp).create_input(threads, trace);
 			const double t2 = now();
 			if (counts)
 			{
 				counts[0] = int64_t(input.num_constraints());
 				counts[2] = input.num_constraints() ? int64_t(input.constraint(0).num_free()) : 0;
 			}
-			if (outdir && *outdir) std::move(input).write(qboot::fs::path(outdir), threads);
+			if (outdir && *outdir) std::move(input).write(qboot::fs::path(outdir), threads, trace);
 			const double t3 = now();
 			if (times)
 			{

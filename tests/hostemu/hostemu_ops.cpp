@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstring>
 
+#include "../../qboot_b200/csrc/polyfx.cuh"
 #include "../../qboot_b200/csrc/mpf.cuh"
 #include "../../qboot_b200/csrc/mpf_math.cuh"
 #include "../../qboot_b200/csrc/fastops.cuh"
@@ -84,6 +85,55 @@ namespace
 	}
 }  // namespace
 
+namespace
+{
+	// the fixed-point evaluation of one polynomial (csrc/polyfx.cuh) at n_count integers; status 1 = fixed point, 0 = the
+	// floating-point Horner fall-back (frame not exact for these coefficients, or a value left the window)
+	template <int L>
+	int poly_fx(int prec, int deg, int nbits, const uint32_t* coefs, int n_count, const uint32_t* ns, uint32_t* out, int32_t* status)
+	{
+		using T = qb::mpf<L>;
+		constexpr int W = L + 2;
+		const T* c = reinterpret_cast<const T*>(coefs);
+		T* O = reinterpret_cast<T*>(out);
+		int32_t e[8];
+		bool have[8];
+		for (int d = 0; d <= deg; ++d)
+		{
+			have[d] = qb::kind(c[d]) == qb::K_REG;
+			e[d] = c[d].exp;
+		}
+		const int32_t E = qb::fx::frame_exponent(e, have, deg, nbits);
+		uint32_t C[8][W], cs[8];
+		bool ok = true;
+		for (int d = 0; d <= deg; ++d) ok = qb::fx::from_record<L>(C[d], cs[d], c[d], E) && ok;
+		for (int i = 0; i < n_count; ++i)
+		{
+			bool good = ok;
+			T p;
+			if (good)
+			{
+				uint32_t V[W], sg = cs[deg];
+				for (int j = 0; j < W; ++j) V[j] = C[deg][j];
+				for (int d = deg - 1; d >= 0 && good; --d) good = qb::fx::horner_step<L>(V, sg, ns[i], C[d], cs[d], prec);
+				if (good) good = qb::fx::to_record<L>(p, V, sg, E);
+			}
+			if (!good)
+			{
+				qb::copy(p, c[deg]);
+				for (int d = deg - 1; d >= 0; --d)
+				{
+					qb::mul_si(p, p, int64_t(ns[i]), prec);
+					qb::add(p, p, c[d], prec);
+				}
+			}
+			O[i] = p;
+			status[i] = good ? 1 : 0;
+		}
+		return 0;
+	}
+}  // namespace
+
 #define QB_FOR_L(X) X(2) X(3) X(4) X(5) X(8) X(16) X(19) X(25) X(32) X(38) X(48)
 
 extern "C" int qbh_op(int prec, int op, int n, const uint32_t* a, const uint32_t* b, const uint32_t* c,
@@ -94,6 +144,20 @@ extern "C" int qbh_op(int prec, int op, int n, const uint32_t* a, const uint32_t
 	{
 #define X(LL) \
 	case LL: return run<LL>(prec, op, n, a, b, c, ia, ib, out, consts);
+		QB_FOR_L(X)
+#undef X
+	default: return -100;
+	}
+}
+
+extern "C" int qbh_poly_fx(int prec, int deg, int nbits, const uint32_t* coefs, int n_count, const uint32_t* ns, uint32_t* out, int32_t* status)
+{
+	int L = (prec + 31) / 32;
+	if (deg < 0 || deg > 7) return -1;
+	switch (L)
+	{
+#define X(LL) \
+	case LL: return poly_fx<LL>(prec, deg, nbits, coefs, n_count, ns, out, status);
 		QB_FOR_L(X)
 #undef X
 	default: return -100;

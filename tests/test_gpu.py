@@ -191,10 +191,11 @@ def test_device_fast_paths_vs_mpfr(ref, prec):
 
 
 def test_chunked_streams_match_single_chunk(tmp_path):
-    """Batches larger than one chunk run their chunks over several streams (wide kernels on one stream, the series
-    recurrences on per-chunk priority streams, finished chunks copied out on a copy stream).  Scheduling must be
-    invisible in the output: a child process with a tiny chunk size (QB_CHUNK is read once per process) must produce
-    the tables of the single-chunk run bit for bit, through both the one-shot call and plan/run/fetch."""
+    """Large batches are cut into chunks, and chunks into front groups, spread over several streams (coefficients + series +
+    powers per group on one stream, scale + Horner per chunk on a second, the transverse recursion on a third, finished
+    chunks copied out on a copy stream).  Scheduling must be invisible in the output: a child process with a tiny chunk and
+    group size (QB_CHUNK / QB_FRONT are read once per process) must produce the tables of the single-chunk run bit for
+    bit, through both the one-shot call and plan/run/fetch."""
     import os
     import subprocess
     import sys
@@ -213,7 +214,7 @@ def test_chunked_streams_match_single_chunk(tmp_path):
         "eng.plan(z['spin'], z['delta'], z['S'], z['P']); eng.run(); eng.sync(); g2 = eng.fetch()\n"
         f"np.savez(r'{tmp_path / 'out.npz'}', g=g, g2=g2, launches=eng.launches)\n"
     )
-    env = dict(os.environ, QB_CHUNK="256", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, QB_CHUNK="256", QB_FRONT="600", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
     out = np.load(tmp_path / "out.npz")
     eng = _engine(prec, n_max, lam)

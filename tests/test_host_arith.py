@@ -351,3 +351,63 @@ def test_fused_horner_step_vs_mpfr(hostemu, ref, prec):
     bad = [i for i in range(len(S)) if not np.array_equal(want[i], out[i])]
     assert not bad, (bad[:5], [int(Nn[i]) for i in bad[:5]])
     assert declined < len(S) // 2   # the fast path takes the bulk (zeros, deep cancellations and the like fall back)
+
+
+@pytest.mark.parametrize("prec", [64, 100, 600, 800, 1000, 1024, 1200, 1536])
+def test_fixed_point_polynomials_vs_mpfr(hostemu, ref, prec):
+    """csrc/polyfx.cuh -- the recurrence polynomials evaluated in a fixed-point frame with the reference's roundings emulated
+    on integers -- against mpfr_mul_ui + mpfr_add Horner (Polynomial::eval, polynomial.hpp:66-83) for n = 1 .. n_lim and
+    beyond, on polynomials shaped like the path's (coefficients of comparable size), with alternating signs (cancellation
+    between the terms), with roots at or next to integers (deep cancellation: must fall back, not be wrong), with zero
+    coefficients, tiny coefficients (not representable in the frame: fall back) and coefficients of few bits (ties)."""
+    from tests.golden.make_golden import rnd_num
+
+    rng = random.Random(prec * 11 + 3)
+    W = words(prec)
+    nbits = 9
+    ns = np.array(list(range(1, 64)) + [100, 127, 128, 255, 256, 399, 400, 401, 500, 511], dtype=np.uint32)
+    fx_used = total = 0
+    for it in range(60):
+        deg = rng.choice([3, 4, 4, 4, 1, 2])
+        style = it % 6
+        cs = []
+        for d in range(deg + 1):
+            if style == 0:      # comparable magnitudes, random signs
+                c = rnd_num(rng, prec, -4, 30)
+            elif style == 1:    # c_d ~ n_typ^-d: every term of the Horner sum has the same size (alternating signs cancel)
+                m = rng.getrandbits(prec) | (1 << (prec - 1))
+                c = ref.from_int_exp(d % 2, m, 20 - 8 * d - prec, prec)
+            elif style == 2:    # few-bit coefficients: products and sums hit ties and exact values
+                m = rng.getrandbits(rng.randint(1, 12)) | 1
+                c = ref.from_int_exp(rng.getrandbits(1), m, rng.randint(-6, 6), prec)
+            elif style == 3:    # one coefficient is zero, one is tiny (2^-300 below the others: outside any frame)
+                c = rnd_num(rng, prec, 0, 8)
+                if d == 1:
+                    c = ref.from_int_exp(0, 0, 0, prec)
+                if d == 0 and it % 12 == 3:
+                    c = rnd_num(rng, prec, -330, -300)
+            elif style == 4:    # (n - r)(...) with an integer root r: exact zeros and neighbours of zero
+                c = None
+            else:
+                c = rnd_num(rng, prec, -40, 40)
+            cs.append(c)
+        if style == 4:
+            r = rng.randint(1, 60)
+            # p(n) = (n - r) (a n^2 + b n + g) with small integer a, b, g: integer coefficients, root at n = r
+            a, b, g = rng.randint(1, 2**20), rng.randint(-2**20, 2**20), rng.randint(-2**20, 2**20)
+            ints = [-r * g, g - r * b, b - r * a, a]
+            deg = 3
+            cs = [ref.from_int_exp(int(v < 0), abs(v), 0, prec) for v in ints]
+        coefs = np.stack(cs)
+        out = np.zeros((len(ns), W), dtype=np.uint32)
+        status = np.zeros(len(ns), dtype=np.int32)
+        assert hostemu.qbh_poly_fx(prec, deg, nbits, P(coefs), len(ns), P(ns), P(out), P(status)) == 0
+        # the reference's Horner, vectorised over n
+        s = np.tile(coefs[deg], (len(ns), 1))
+        for d in range(deg - 1, -1, -1):
+            s = ref.op("add", prec, a=ref.op("mul_si", prec, a=s, ia=ns.astype(np.int64)), b=np.tile(coefs[d], (len(ns), 1)))
+        bad = [int(ns[i]) for i in range(len(ns)) if not np.array_equal(s[i], out[i])]
+        assert not bad, (it, style, bad[:5])
+        fx_used += int(status.sum())
+        total += len(ns)
+    assert fx_used > total // 2   # the fixed-point path carries the bulk; the rest fell back (and is still exact)
