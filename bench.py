@@ -47,6 +47,18 @@ WORKLOAD = ("gBlock tables, Context(n_Max=400, lambda=19, dim=3), 1024-bit, mixe
 TOTAL_TABLES = 392768  # 8 x 49 096: 64 grid points of the 13 x 13 scan (a fixed total for every N: strong scaling)
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -117,7 +129,7 @@ def run_reference(args, rank, world):
     from oracle import ref
 
     if not ref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libqboot_ref.so not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libqboot_ref.so not built (needs /root/reference at build time)"})
         return 0
     cores = host_cores()
     sample = int(args.ref_tables) if args.ref_tables else max(64, 16 * cores)
@@ -141,7 +153,7 @@ def run_reference(args, rank, world):
     }
     if not args.no_pmp:
         line["pmp_build"] = {"single": ref_pmp(0, cores), "mixed": ref_pmp(1, cores)}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -225,6 +237,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pmp", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything else a library may print there (NCCL's version banner,
+    # torchrun notices) is sent to stderr for the lifetime of the process
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rules: at least 3 warm-up steps
 
@@ -486,7 +505,7 @@ def main():
             line["pmp_build"] = pmp_leg(host_cores(), ref.available() and not args.no_cpu_baseline)
         except Exception as ex:
             line["pmp_build"] = {"error": str(ex)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -62,7 +62,7 @@ def raw(path):
         k = short(r[ki])
         if k not in seen or float(r[gi].replace(",", "")) > float(seen[k][gi].replace(",", "")):
             seen[k] = r
-    order = ["k_rec_coeffs", "k_polyvals", "k_pow", "k_series", "k_scale", "k_horner", "k_rho_to_z", "k_offdiag_val", "k_offdiag_close"]
+    order = ["k_rec_coeffs", "k_coef_fx", "k_series", "k_pow", "k_scale", "k_horner", "k_rho_to_z", "k_offdiag_val", "k_offdiag_close"]
     names = sorted(seen, key=lambda n: next((i for i, o in enumerate(order) if n.startswith(o)), 99))
     print("metric".ljust(46) + "".join(n[:17].rjust(18) for n in names))
     for key, label in KEYS:
