@@ -208,15 +208,14 @@ def pmp_leg(cores: int, with_reference: bool):
 
 
 def ncu_traffic(n_tables):
-    """DRAM bytes per launch of the dominant stage from the committed ncu --set full capture (profiles/), scaled from the
-    captured launch's table count to this run's chunk size; None when no capture is recorded."""
-    for name in ("r2_traffic.json", "r1_traffic.json"):
-        try:
-            rec = json.load(open(os.path.join(ROOT, "profiles", name)))
-            return rec["deriv_dram_bytes_per_table"] * min(n_tables, rec.get("chunk_tables", n_tables))
-        except Exception:
-            continue
-    return None
+    """DRAM bytes of one step from the committed ncu --set full capture (profiles/r2_traffic.json: dram__bytes_read.sum +
+    dram__bytes_write.sum of every pipeline kernel, per table), scaled to this run's tables per step; None when no capture
+    is recorded."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        return rec["step_dram_bytes_per_table"] * n_tables
+    except Exception:
+        return None
 
 
 class _DevBytes:
@@ -456,7 +455,9 @@ def main():
         "kernel_ms_per_step": {"rec_coeffs": float(kms[0]), "series": float(kms[1]), "deriv": float(kms[2]), "finish": float(kms[3]),
                                "note": "chunks serialised on one stream with an event around every stage; the timed step overlaps them"},
         "roofline": {"bound": "imad", "achieved": step_frac * peak / 1e12, "peak": peak / 1e12, "unit": "Tlimb-MAC/s", "frac": step_frac,
-                     "traffic": ncu_traffic(n), "kernel": "whole step (k_rec_coeffs, k_series, k_pow, k_scale, k_horner, k_rho_to_z, k_offdiag_*)",
+                     "traffic": ncu_traffic(n), "traffic_note": "DRAM bytes per step per GPU from the ncu capture of every kernel (profiles/r2_traffic.json); "
+                                                                "the path is multiply-bound, not HBM-bound: ~7.4 MB per table against 2.3e7 limb-MACs",
+                     "kernel": "whole step (k_rec_coeffs, k_series, k_pow, k_scale, k_horner, k_rho_to_z, k_offdiag_*)",
                      "stages": stages,
                      "peak_source": "measured on this GPU by qb_imad_peak: dependency-free IMAD.WIDE.U32 chains at full occupancy "
                                     "(32 x 32 + 64 -> 64; issues at 32 per clock per SM, half the 32-bit IMAD rate)",

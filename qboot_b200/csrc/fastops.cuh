@@ -312,10 +312,13 @@ namespace qb
 		// the two undecidable cases (probability ~L 2^-32 for full-width operands) the function returns false and the caller
 		// takes the full product.  A short multiplicand b (all limbs below position L - 5 zero) is recognised: then nothing
 		// nonzero was skipped and f4 = f5 = 0 means an exact frame.  st: as mul_top.
+#ifndef QB_SHORT_ROWS
+#define QB_SHORT_ROWS 8  // rows per staircase segment (even)
+#endif
 		template <int L>
 		struct ShortPlan
 		{
-			static constexpr int LP = (L + 1) & ~1, T = L - 5, R = 8, NSEG = (LP + R - 1) / R;
+			static constexpr int LP = (L + 1) & ~1, T = L - 5, R = QB_SHORT_ROWS, NSEG = (LP + R - 1) / R;
 			static constexpr int i0(int s) { return s * R; }
 			static constexpr int i1(int s) { return (s * R + R < LP) ? s * R + R : LP; }
 			static constexpr int kmin(int s) { return T - (i1(s) - 1) <= 0 ? 0 : ((T - (i1(s) - 1)) & ~1); }
