@@ -390,6 +390,30 @@ def main():
         kms += np.array(eng.kernel_times())
     kms /= ksteps  # per step
 
+    # ---- F/H blocks over the resident tables (Context::F_block / evaluate): terms per second through
+    # qb_fblock_batch, results to the host (N = 1; inside a PMP build the same products are fused into k_pmp_accum) -------
+    fblock = None
+    if world == 1:
+        import ctypes as C
+
+        m = min(n, 32768)
+        t_idx = np.ascontiguousarray(np.arange(m, dtype=np.int32) * (n // m))
+        dvals = np.stack([qb.from_str("0.5181489", PREC), qb.from_str("0.96543695", PREC), qb.from_str("1.412625", PREC)])
+        d_idx = np.ascontiguousarray(np.arange(m, dtype=np.int32) % 3)
+        sym = np.ascontiguousarray(np.arange(m, dtype=np.int32) % 2)
+        dims = [eng.lib.qb_block_dim(eng.h, 0), eng.lib.qb_block_dim(eng.h, 1)]
+        f_out = np.zeros((int(sum(dims[int(s)] for s in sym)), W), dtype=np.uint32)
+        P_ = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        for rep in range(3):
+            t0 = time.perf_counter()
+            eng._check(eng.lib.qb_fblock_batch(eng.h, m, P_(t_idx), len(dvals), P_(dvals), P_(d_idx), P_(sym), P_(f_out)), "qb_fblock_batch")
+            t_f = time.perf_counter() - t0
+        pairs = 2640  # Mixed x Mixed products per term at lambda = 19
+        fblock = {"terms": int(m), "terms_per_s": m / t_f, "ms": 1e3 * t_f, "d2h_bytes": int(f_out.nbytes),
+                  "limb_macs_per_term": pairs * 32 * 32, "frac_of_peak": m * pairs * 32 * 32 / t_f / peak,
+                  "note": "wall clock of the C-ABI call: upload of the term list, k_vtod + k_fblock, results copied to pageable host memory"}
+        del f_out
+
     # ---- end-to-end leg: host buffers in, host buffers out, through the one-shot C-ABI call ------------------------------
     lib, h = eng.lib, eng.h
     import ctypes as C
@@ -495,6 +519,8 @@ def main():
                                         "against": "unmodified reference (oracle/_ref) on the same keys"}
         except Exception as ex:  # the baseline is reported, never required
             line["cpu_baseline"] = {"error": str(ex)}
+    if fblock is not None:
+        line["fblock"] = fblock
     if world == 1 and not args.no_pmp:
         # M2.  The table engine's buffers are released first: the facade owns its own handle
         del h_out

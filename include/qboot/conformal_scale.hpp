@@ -34,9 +34,22 @@ namespace qboot
 		std::optional<mp::real> end_;
 		algebra::Vector<mp::real> poles_;  // 1 / (Delta - poles_[i]), largest first
 		algebra::Vector<algebra::Polynomial> bilinear_bases_{};
+		bool bases_ready_ = true;
 		void _set_bilinear_bases() &;
 
 	public:
+		// The planner of BootstrapEquation::convert only needs the poles and the sample points before the GPU can start; the
+		// bilinear bases (incomplete gamma functions, a Hankel-Cholesky factorisation: most of the constructor's time) are
+		// then built on host threads underneath the GPU phase.  _finish_bases() must run before bilinear_bases() is used.
+		struct _DeferBases
+		{
+		};
+		ConformalScale(_DeferBases, const GeneralPrimaryOperator& op, const Context& context, bool include_odd);
+		void _finish_bases() &
+		{
+			if (!bases_ready_) _set_bilinear_bases();
+			bases_ready_ = true;
+		}
 		void _reset() &&
 		{
 			odd_included_ = false;

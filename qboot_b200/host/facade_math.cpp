@@ -328,6 +328,13 @@ namespace qboot
 	    : ConformalScale(op.num_poles(), op.spin(), c, include_odd, op.lower_bound(), op.upper_bound_safe())
 	{
 	}
+	ConformalScale::ConformalScale(_DeferBases, const GeneralPrimaryOperator& op, const Context& c, bool include_odd)
+	    : odd_included_(include_odd), spin_(op.spin()), lambda_(c.lambda()), epsilon_(c.epsilon()), rho_(c.rho()), gap_(op.lower_bound()),
+	      end_(op.upper_bound_safe()), poles_(op.num_poles()), bilinear_bases_((op.num_poles() + c.lambda()) / 2 + 1), bases_ready_(false)
+	{
+		PoleFamily fam[3] = {PoleFamily(1, spin_, epsilon_, include_odd), PoleFamily(2, spin_, epsilon_, include_odd), PoleFamily(3, spin_, epsilon_, include_odd)};
+		for (uint32_t i = 0; i < poles_.size(); ++i) poles_[i] = real(next_pole(fam));
+	}
 	// include/qboot/conformal_scale.hpp:66-72
 	real ConformalScale::eval_d(const real& delta) const
 	{

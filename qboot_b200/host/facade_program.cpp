@@ -162,7 +162,8 @@ namespace qboot
 					tasks.emplace_back([this, &it, &event] {
 						const auto& op = be.sector(it.sector).ops_[size_t(it.op_index)];
 						_scoped_event scope(op.str() + " in " + be.sector(it.sector).name(), event);
-						it.scale = be.common_scale(it.sector, op);
+						// poles and sample points now; the bilinear bases follow underneath the GPU phase (convert)
+						it.scale = std::make_unique<ConformalScale>(ConformalScale::_DeferBases{}, op, be.cont_, be.sector_includes_odd(it.sector));
 						auto xs = it.scale->sample_points();
 						it.deltas = Vector<real>(xs.size());
 						for (uint32_t k = 0; k < xs.size(); ++k) it.deltas[k] = it.scale->get_delta(xs[k]);
@@ -382,6 +383,7 @@ namespace qboot
 			for (auto& it : plan.items)
 				if (it.op_index >= 0 && it.scale)
 					tasks.emplace_back([&it] {
+						it.scale->_finish_bases();
 						it.bilinear = bilinear_at_samples(*it.scale);
 						return 0;
 					});
