@@ -458,6 +458,13 @@ def main():
 
     ms_per_step = dev_ms / args.steps
     value = total_tables / (ms_per_step * 1e-3)
+    # distinct keys of the step: the scan re-emits the even sector's keys (S = P = 0, Delta independent of the grid
+    # point) at every grid point; the table kernels compute what they are handed -- the façade's planner is what dedupes
+    unique_tables = None
+    if world == 1:
+        rows = np.ascontiguousarray(np.concatenate([spin.astype(np.uint32)[:, None], delta, S, P], axis=1))
+        unique_tables = int(len(np.unique(rows.view(np.dtype((np.void, rows.dtype.itemsize * rows.shape[1]))))))
+        del rows
     in_bytes = int(spin.nbytes + delta.nbytes + S.nbytes + P.nbytes)
     out_bytes = int(n * table_bytes)
     stage_names = ("rec", "series", "deriv", "finish")
@@ -470,7 +477,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f1024 (32 x u32 limbs, round-to-nearest-even per operation)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "total_tables_per_step": int(total_tables), "tables_per_gpu_per_step": n, "precision_bits": PREC,
+        "config": {"workload": WORKLOAD, "total_tables_per_step": int(total_tables), "tables_per_gpu_per_step": n,
+                   "distinct_keys_per_step": unique_tables, "precision_bits": PREC,
                    "n_Max": N_MAX, "lambda": LAM, "sharding": "keys sorted by cost class (spin 0 / spin > 0), dealt round-robin to the ranks",
                    "l2": "each step rewrites its %d MB of tables and %d MB of series coefficients (> 126 MB L2)" % (
                        out_bytes // 2**20, n * (N_MAX + 1) * W * 4 // 2**20)},

@@ -52,12 +52,26 @@ namespace qb
 	                         const mpf<QB_L>* coef, const uint32_t* coefx, mpf<QB_L>* b, cudaStream_t st)
 	{
 		static const bool attr_set = [] {
-			cudaFuncSetAttribute(k_series<QB_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(series_smem_bytes<QB_L>()));
+			cudaFuncSetAttribute(k_series<QB_L, QB_SERIES_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                     int(series_smem_bytes<QB_L, QB_SERIES_THREADS>()));
+			cudaFuncSetAttribute(k_series<QB_L, QB_SERIES_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                     int(series_smem_bytes<QB_L, QB_SERIES_THREADS_SMALL>()));
 			return true;
 		}();
 		(void)attr_set;
-		k_series<QB_L><<<(n_jobs + QB_SERIES_THREADS - 1) / QB_SERIES_THREADS, QB_SERIES_THREADS, series_smem_bytes<QB_L>(), st>>>(cx, n_jobs, delta, spin, b0,
-		                                                                                                                      coef, coefx, b);
+		static const int sms = [] {
+			int dev = 0, n = 148;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+			return n;
+		}();
+		// at most one small CTA per SM: the small-CTA kernel (one warp per scheduler); otherwise the large lockstep CTAs
+		if (n_jobs <= sms * QB_SERIES_THREADS_SMALL)
+			k_series<QB_L, QB_SERIES_THREADS_SMALL><<<(n_jobs + QB_SERIES_THREADS_SMALL - 1) / QB_SERIES_THREADS_SMALL, QB_SERIES_THREADS_SMALL,
+			                                         series_smem_bytes<QB_L, QB_SERIES_THREADS_SMALL>(), st>>>(cx, n_jobs, delta, spin, b0, coef, coefx, b);
+		else
+			k_series<QB_L, QB_SERIES_THREADS><<<(n_jobs + QB_SERIES_THREADS - 1) / QB_SERIES_THREADS, QB_SERIES_THREADS,
+			                                   series_smem_bytes<QB_L, QB_SERIES_THREADS>(), st>>>(cx, n_jobs, delta, spin, b0, coef, coefx, b);
 	}
 #elif QB_KGROUP == 2
 	template <>

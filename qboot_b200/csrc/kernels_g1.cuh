@@ -99,39 +99,42 @@ namespace qb
 #define QB_SERIES_T 384
 #endif
 	constexpr int QB_SERIES_THREADS = QB_SERIES_T;
-	template <int L>
+	// small batches (a single PMP: 1-6 k jobs) run CTAs of 128 threads instead: one warp per scheduler on as many SMs as the
+	// batch reaches -- a step of a lone warp takes a third of a step among twelve
+	constexpr int QB_SERIES_THREADS_SMALL = 128;
+	template <int L, int T>
 	constexpr size_t series_smem_bytes()
 	{
-		return size_t(2) * L * QB_SERIES_THREADS * sizeof(uint32_t);
+		return size_t(2) * L * T * sizeof(uint32_t);
 	}
-	template <int L>
+	template <int L, int T>
 	__device__ __forceinline__ void series_store(uint32_t* my, uint32_t& sk, int32_t& exp, const mpf<L>& v)
 	{
 		sk = v.sk;
 		exp = v.exp;
 #pragma unroll
-		for (int j = 0; j < L; ++j) my[j * QB_SERIES_THREADS] = v.m[j];
+		for (int j = 0; j < L; ++j) my[j * T] = v.m[j];
 	}
-	template <int L>
+	template <int L, int T>
 	__device__ __forceinline__ void series_load(mpf<L>& v, const uint32_t* my, uint32_t sk, int32_t exp)
 	{
 		v.sk = sk;
 		v.exp = exp;
 #pragma unroll
-		for (int j = 0; j < L; ++j) v.m[j] = my[j * QB_SERIES_THREADS];
+		for (int j = 0; j < L; ++j) v.m[j] = my[j * T];
 	}
 #ifndef QB_SERIES_CTAS
 #define QB_SERIES_CTAS 1
 #endif
-	template <int L>
-	__global__ void __launch_bounds__(QB_SERIES_THREADS, QB_SERIES_CTAS)
+	template <int L, int T>
+	__global__ void __launch_bounds__(T, QB_SERIES_CTAS)
 	    k_series(DevCtx cx, int n_jobs, const mpf<L>* __restrict__ delta, const uint32_t* __restrict__ spin, const mpf<L>* __restrict__ b0,
 	             const mpf<L>* __restrict__ coef, const uint32_t* __restrict__ coefx, mpf<L>* __restrict__ b)
 	{
 		extern __shared__ uint32_t sh[];
 		uint32_t* myp = sh + threadIdx.x;                           // p_i(n)
-		uint32_t* mys = sh + L * QB_SERIES_THREADS + threadIdx.x;   // running sum
-		const int job = blockIdx.x * QB_SERIES_THREADS + threadIdx.x;
+		uint32_t* mys = sh + L * T + threadIdx.x;   // running sum
+		const int job = blockIdx.x * T + threadIdx.x;
 		const int prec = cx.prec;
 		const uint32_t n_max = cx.n_max;
 		bool active = job < n_jobs;
@@ -240,7 +243,7 @@ namespace qb
 				{
 					// b[n] = -sum / p_0(n)
 					mpf<L> sum, bn;
-					series_load(sum, mys, ssk, sexp);
+					series_load<L, T>(sum, mys, ssk, sexp);
 					neg(sum);
 					fast::div(bn, sum, p, prec);
 					copy(bj[n], bn);
@@ -251,10 +254,10 @@ namespace qb
 				bool done = false;
 				if ((p.sk & 3u) == K_REG && (bp.sk & 3u) == K_REG && (i == 1 || (ssk & 3u) == K_REG))
 				{
-					series_store(myp, psk, pexp, p);
+					series_store<L, T>(myp, psk, pexp, p);
 					uint32_t X[L + 3], stt;
 					int32_t e;
-					fast::product_frame<L, QB_SERIES_THREADS>(X, stt, e, myp, pexp, bp);
+					fast::product_frame<L, T>(X, stt, e, myp, pexp, bp);
 					const uint32_t sgn = (psk ^ bp.sk) & SIGN_BIT;
 					mpf<L> r;
 					if (i == 1)
@@ -262,10 +265,10 @@ namespace qb
 					else
 					{
 						mpf<L> sum;
-						series_load(sum, mys, ssk, sexp);
+						series_load<L, T>(sum, mys, ssk, sexp);
 						done = fast::addround<L>(r, sgn, e, X + 1, stt, sum, prec);
 					}
-					if (done) series_store(mys, ssk, sexp, r);
+					if (done) series_store<L, T>(mys, ssk, sexp, r);
 				}
 				if (!done)
 				{
@@ -275,10 +278,10 @@ namespace qb
 						fast::cold_mul(r, p, bp, prec);
 					else
 					{
-						series_load(sum, mys, ssk, sexp);
+						series_load<L, T>(sum, mys, ssk, sexp);
 						fast::cold_fma(r, p, bp, sum, prec);
 					}
-					series_store(mys, ssk, sexp, r);
+					series_store<L, T>(mys, ssk, sexp, r);
 				}
 			}
 		}
