@@ -211,6 +211,17 @@ int qb_pmp_text_patch(qb_handle* h, int cnt, const int64_t* idx, const char* tex
 int qb_pmp_text_fetch(qb_handle* h, char* out);
 /* out[0] blocks in the arena, [1] N, [2] records in the arena, [3] selected blocks of the last pack */
 int qb_pmp_info(const qb_handle* h, int64_t* out4);
+/* Bilinear bases at the sample points -- the other half of PolynomialProgram::create_input (src/polynomial_program.cpp:224-229):
+ *   out[i] = RN( eval(poly[items[i].poly], x[items[i].x]) * s[items[i].s] )
+ * with eval = Horner's rule by fused multiply-adds, exactly Polynomial::eval with a real argument
+ * (include/qboot/algebra/polynomial.hpp:66-83).  Polynomial p has the coefficients coef[poly_ofs[p] .. poly_ofs[p + 1]) (constant
+ * term first; none = the zero polynomial).  Everything HOST memory in, n_items records out.  Needs a context. */
+typedef struct qb_eval_item
+{
+	int32_t poly, x, s;
+} qb_eval_item;
+int qb_poly_eval_batch(qb_handle* h, int n_polys, const int32_t* poly_ofs, const uint32_t* coef, int n_x, const uint32_t* x, int n_s,
+                       const uint32_t* s, int n_items, const qb_eval_item* items, uint32_t* out);
 /* Diagnostic: n numbers (HOST) formatted on the device into slots of `slot` >= ndigits + 16 bytes; len[i] = bytes used
  * or a negative code when declined (see format_decimal in qboot_b200/csrc/pmp.cuh). */
 int qb_dec_format(qb_handle* h, int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* len);

@@ -22,7 +22,7 @@ SYMBOLS = (
     "qb_stream", "qb_fblock_batch", "qb_op_batch", "qb_set_timing", "qb_kernel_times", "qb_imad_peak",
     "qb_vtod_batch", "qb_fblock_tables", "qb_pinned_alloc", "qb_pinned_free",
     "qb_pmp_assemble", "qb_pmp_block_add", "qb_pmp_block_fetch", "qb_pmp_pack", "qb_pmp_packed_fetch", "qb_pmp_text",
-    "qb_pmp_text_declined", "qb_pmp_text_patch", "qb_pmp_text_fetch", "qb_pmp_info", "qb_dec_format",
+    "qb_pmp_text_declined", "qb_pmp_text_patch", "qb_pmp_text_fetch", "qb_pmp_info", "qb_dec_format", "qb_poly_eval_batch",
     "qb_set_ziv_slack", "qb_ziv_counters",
     "qb_gblock_set_sink", "qb_device_alloc", "qb_device_free", "qb_ipc_export", "qb_ipc_open", "qb_ipc_close",
 )
@@ -94,6 +94,8 @@ def load_library():
     lib.qb_pmp_text_fetch.argtypes = [C.c_void_p, C.c_void_p]
     lib.qb_pmp_info.argtypes = [C.c_void_p, C.c_void_p]
     lib.qb_dec_format.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.qb_poly_eval_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p]
     lib.qb_gblock_set_sink.argtypes = [C.c_void_p, C.c_void_p]
     lib.qb_device_alloc.argtypes = [C.c_void_p, C.c_size_t]
     lib.qb_device_alloc.restype = C.c_void_p

@@ -346,6 +346,13 @@ extern "C"
 	}
 	int qb_pmp_text_fetch(qb_handle* h, char* out) { QB_GUARDED(h ? h->e->pmp_text_fetch(out) : QB_ERR_BAD_ARG) }
 	int qb_pmp_info(const qb_handle* h, int64_t* out4) { return (h && out4) ? h->e->pmp_info(out4) : QB_ERR_BAD_ARG; }
+	static_assert(sizeof(qb_eval_item) == 12, "qb_eval_item layout: three int32, as qb::EvalItem (pmp_types.cuh)");
+	int qb_poly_eval_batch(qb_handle* h, int n_polys, const int32_t* poly_ofs, const uint32_t* coef, int n_x, const uint32_t* x, int n_s,
+	                       const uint32_t* s, int n_items, const qb_eval_item* items, uint32_t* out)
+	{
+		QB_GUARDED(h ? h->e->poly_eval_batch(n_polys, poly_ofs, coef, n_x, x, n_s, s, n_items, reinterpret_cast<const int32_t*>(items), out)
+		             : QB_ERR_BAD_ARG)
+	}
 	int qb_dec_format(qb_handle* h, int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* len)
 	{
 		QB_GUARDED(h ? h->e->dec_format(ndigits, n, x, slots, slot, len) : QB_ERR_BAD_ARG)

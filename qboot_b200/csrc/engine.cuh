@@ -63,6 +63,8 @@ namespace qb
 		virtual int pmp_text_fetch(char* out) = 0;
 		virtual int pmp_info(int64_t* out4) const = 0;
 		virtual int dec_format(int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* len) = 0;
+		virtual int poly_eval_batch(int n_polys, const int32_t* poly_ofs, const uint32_t* coef, int n_x, const uint32_t* x, int n_s,
+		                            const uint32_t* s, int n_items, const int32_t* items3, uint32_t* out) = 0;
 		// Ziv loop of the powers: width of the in-doubt window (0 = default) and the counters [second-level evaluations,
 		// values still in doubt] since the handle was created
 		virtual int set_ziv_slack(int bits) = 0;

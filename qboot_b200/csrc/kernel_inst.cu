@@ -143,6 +143,13 @@ namespace qb
 		                                                                                Carena, total);
 	}
 	template <>
+	void launch_poly_eval<QB_L>(const DevCtx& cx, int n_items, const EvalItem* items, const int32_t* poly_ofs, const mpf<QB_L>* coef,
+	                            const mpf<QB_L>* x, const mpf<QB_L>* s, mpf<QB_L>* out, cudaStream_t st)
+	{
+		const int threads = 128;
+		k_poly_eval<QB_L><<<(n_items + threads - 1) / threads, threads, 0, st>>>(cx, n_items, items, poly_ofs, coef, x, s, out);
+	}
+	template <>
 	void launch_dec_format<QB_L>(const DecTables& tb, int64_t n, const mpf<QB_L>* x, char* slots, int slot, int32_t* len, cudaStream_t st)
 	{
 		const int threads = 64;

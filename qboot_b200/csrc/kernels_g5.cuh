@@ -4,6 +4,7 @@
 //                a warp evaluate the SAME entry of the same terms at 32 different sample points, so they walk identical
 //                loops (F-block dot products of equal length) over different block tables         -> M[block][p][n]
 //   k_pmp_pack   one thread per (block, row p, free variable m | the d_c column), m fastest         -> d_B, d_c
+//   k_poly_eval  one thread per (polynomial, point, scale): fma Horner, then the scale                -> out
 //   k_dec_format one thread per number: decimal digits + layout into a fixed-size slot              -> slots, lengths
 //   k_dec_gather one warp per number: slot -> its final place in the contiguous text               -> text
 #pragma once
@@ -73,6 +74,21 @@ namespace qb
 			copy(Barena[blk.ofs_b + p * n_free + m], r);
 		else
 			copy(Carena[blk.ofs_c + p], r);
+	}
+
+	// polynomials at points, scaled (bilinear bases at the sample points): one thread per item
+	template <int L>
+	__global__ void k_poly_eval(DevCtx cx, int n_items, const EvalItem* __restrict__ items, const int32_t* __restrict__ poly_ofs,
+	                            const mpf<L>* __restrict__ coef, const mpf<L>* __restrict__ x, const mpf<L>* __restrict__ s,
+	                            mpf<L>* __restrict__ out)
+	{
+		const int i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i >= n_items) return;
+		const EvalItem it = items[i];
+		const int o = poly_ofs[it.poly], deg = poly_ofs[it.poly + 1] - o - 1;
+		mpf<L> r;
+		poly_eval_scaled<L>(r, coef + o, deg, x[it.x], s[it.s], cx.prec);
+		copy(out[i], r);
 	}
 
 	// numbers -> text slots of `slot` bytes each; len[i] = bytes used, or < 0 when the host has to format number i

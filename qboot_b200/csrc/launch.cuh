@@ -110,6 +110,9 @@ namespace qb
 	                     int n_elim, const int32_t* lead, const mpf<L>* eqn, const mpf<L>* eqn_target, const mpf<L>* Marena,
 	                     const mpf<L>* targets, mpf<L>* Barena, mpf<L>* Carena, int64_t total, cudaStream_t st);
 	template <int L>
+	void launch_poly_eval(const DevCtx& cx, int n_items, const EvalItem* items, const int32_t* poly_ofs, const mpf<L>* coef, const mpf<L>* x,
+	                      const mpf<L>* s, mpf<L>* out, cudaStream_t st);
+	template <int L>
 	void launch_dec_format(const DecTables& tb, int64_t n, const mpf<L>* x, char* slots, int slot, int32_t* len, cudaStream_t st);
 	void launch_dec_gather(int64_t n, const char* slots, int slot, const int32_t* len, const int64_t* ofs, char* text, cudaStream_t st);
 	// integer multiply-add probe (capi.cu)

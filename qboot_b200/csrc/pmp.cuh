@@ -89,6 +89,29 @@ namespace qb
 		copy(out, acc);
 	}
 
+	// out = RN(eval(c[0 .. deg], x) * s): Horner with fused multiply-adds, exactly Polynomial::eval with a real argument
+	// (include/qboot/algebra/polynomial.hpp:66-83), then one product -- an entry q_m(x_k) sqrt(s_k) of the bilinear bases at
+	// the sample points (src/polynomial_program.cpp:224-229).  deg < 0: the zero polynomial.  c, x, s anywhere; out thread-local
+	template <int L>
+	QB_HD QB_NOINLINE void poly_eval_scaled(mpf<L>& out, const mpf<L>* c, int deg, const mpf<L>& x, const mpf<L>& s, int prec)
+	{
+		mpf<L> acc, xx, cc, ss;
+		if (deg < 0)
+			set_zero(acc);
+		else
+		{
+			copy(acc, c[deg]);
+			copy(xx, x);
+			for (int i = deg - 1; i >= 0; --i)
+			{
+				copy(cc, c[i]);
+				fast::fma(acc, acc, xx, cc, prec);
+			}
+		}
+		copy(ss, s);
+		fast::mul(out, acc, ss, prec);
+	}
+
 	// ---- decimal text ---------------------------------------------------------------------------------------------------
 	QB_HD QB_INLINE uint32_t pow5_small(int b)
 	{

@@ -29,6 +29,12 @@ namespace qb
 	};
 	QB_HD QB_INLINE int pmp_schur(const PmpBlock& b) { return b.n_samples * (b.sz * (b.sz + 1) / 2); }
 
+	// one entry of qb_poly_eval_batch: polynomial, argument and scale by index
+	struct EvalItem
+	{
+		int32_t poly, x, s;
+	};
+
 	// Tables for format_decimal, built on the host for one (L, ndigits): powers of five in two levels
 	//   5^k = P13[k / 13] * 5^(k % 13),  P13[a] = 5^(13 a) as little-endian limbs (length plen[a], offset pofs[a])
 	// and the bounds 10^ndigits, 10^(ndigits-1) as L + 2 limbs.

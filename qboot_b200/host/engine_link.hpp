@@ -68,5 +68,6 @@ namespace qboot::b200
 	void pinned_release(char* p, size_t bytes);
 	// n numbers (records, host) -> their SDPB text lines, formatted on the device (qb_dec_format) with the host formatter
 	// for the few the device declines; appended to `out`
-	void format_numbers(Engine& e, int ndigits, const uint32_t* recs, size_t n, std::string& out);
+	// (ends, when given, receives the offset in `out` just past each number's line)
+	void format_numbers(Engine& e, int ndigits, const uint32_t* recs, size_t n, std::string& out, std::vector<size_t>* ends = nullptr);
 }  // namespace qboot::b200

@@ -112,12 +112,14 @@ namespace qboot
 			}
 			qb_pinned_free(drop);
 		}
-		void format_numbers(Engine& e, int ndigits, const uint32_t* recs, size_t n, std::string& out)
+		void format_numbers(Engine& e, int ndigits, const uint32_t* recs, size_t n, std::string& out, std::vector<size_t>* ends)
 		{
+			if (ends) ends->reserve(ends->size() + n);
 			if (n == 0) return;
 			const int slot = ndigits + 16;
 			std::vector<char> slots(n * size_t(slot));
 			std::vector<int32_t> len(n);
+			out.reserve(out.size() + n * size_t(ndigits + 8));
 			{
 				std::lock_guard<std::recursive_mutex> g(e.mu);
 				e.check(qb_dec_format(e.h, ndigits, int(n), recs, slots.data(), slot, len.data()), "qb_dec_format");
@@ -133,6 +135,7 @@ namespace qboot
 					out += mp::_format(r, std::ios_base::fmtflags{}, ndigits);
 					out += '\n';
 				}
+				if (ends) ends->push_back(out.size());
 			}
 		}
 	}  // namespace b200

@@ -138,7 +138,8 @@ namespace qboot
 			int32_t op_index;                      // -1: discrete sector
 			unique_ptr<ConformalScale> scale;      // continuous only
 			Vector<real> deltas;                   // sample Deltas (continuous only)
-			std::optional<std::array<Matrix<real>, 2>> bilinear{};  // q_m(x_k) sqrt(s_k [x_k]), computed while the GPU works
+			std::optional<std::array<Matrix<real>, 2>> bilinear{};  // q_m(x_k) sqrt(s_k [x_k])
+			std::shared_ptr<void> samples{};                         // BilinearSamples, prepared while the GPU works
 		};
 		const BootstrapEquation& be;
 		std::shared_ptr<b200::Engine> engine;
@@ -329,7 +330,13 @@ namespace qboot
 	{
 		throw std::logic_error("qboot_b200: get_spectrum (extremal functional method) is outside the scope of this engine");
 	}
-	static std::array<Matrix<real>, 2> bilinear_at_samples(const ScaleFactor& chi);
+	struct BilinearSamples
+	{
+		Vector<real> xs, s0, s1;  // sample points, sqrt(s_k), sqrt(s_k x_k)
+	};
+	BilinearSamples prepare_bilinear_samples(const ScaleFactor& chi);
+	static vector<std::array<Matrix<real>, 2>> bilinear_at_samples_batch(b200::Engine& eng, const vector<const ScaleFactor*>& chis,
+	                                                                    const vector<const BilinearSamples*>& samples);
 	// src/bootstrap_equation.cpp:555-593, batched
 	PolynomialProgram BootstrapEquation::convert(const unique_ptr<SDPMode>& mode, uint32_t parallel, const unique_ptr<_event_base>& event) const
 	{
@@ -364,8 +371,8 @@ namespace qboot
 		}
 		plan.build_terms();
 		{
-			// The GPU computes the tables and assembles the constraint blocks while the host threads evaluate the bilinear bases
-			// at the sample points (create_input's other half: independent of the tables, src/polynomial_program.cpp:224-229).
+			// The GPU computes the tables and assembles the constraint blocks while the host threads build the bilinear bases of
+			// the scale factors (incomplete gamma functions, Hankel-Cholesky: independent of the tables).
 			_scoped_event scope("tables + assembly (GPU) | bilinear bases (host)", event);
 			std::exception_ptr gpu_error;
 			std::thread gpu([&] {
@@ -384,12 +391,13 @@ namespace qboot
 				if (it.op_index >= 0 && it.scale)
 					tasks.emplace_back([&it] {
 						it.scale->_finish_bases();
-						it.bilinear = bilinear_at_samples(*it.scale);
+						it.samples = std::make_shared<BilinearSamples>(prepare_bilinear_samples(*it.scale));
 						return 0;
 					});
 			try
 			{
-				_parallel_evaluate(tasks, std::max(parallel, cont_.parallel()));
+				// one hardware thread is left to the thread that drives the GPU
+				_parallel_evaluate(tasks, std::max(1u, std::max(parallel, cont_.parallel()) - 1));
 			}
 			catch (...)
 			{
@@ -398,6 +406,22 @@ namespace qboot
 			}
 			gpu.join();
 			if (gpu_error) std::rethrow_exception(gpu_error);
+		}
+		{
+			// the bases at the sample points: one more device batch (create_input's other half, src/polynomial_program.cpp:224-229)
+			_scoped_event scope("bilinear bases at the sample points (GPU)", event);
+			vector<const ScaleFactor*> chis;
+			vector<const BilinearSamples*> smp;
+			for (auto& it : plan.items)
+				if (it.op_index >= 0 && it.scale)
+				{
+					chis.push_back(it.scale.get());
+					smp.push_back(static_cast<const BilinearSamples*>(it.samples.get()));
+				}
+			auto bl = bilinear_at_samples_batch(*plan.engine, chis, smp);
+			size_t i = 0;
+			for (auto& it : plan.items)
+				if (it.op_index >= 0 && it.scale) it.bilinear = move(bl[i++]);
 		}
 		// discrete sectors come back to the host: the mode's normalisation / objective vectors are built from them
 		disc_cache_.clear();
@@ -595,21 +619,77 @@ namespace qboot
 		return {move(constant), move(obj_new)};
 	}
 	// bilinear bases at the sample points (src/polynomial_program.cpp:224-229): q0[m][k] = q_m(x_k) sqrt(s_k),
-	// q1[m][k] = q_m(x_k) sqrt(s_k x_k)
-	static std::array<Matrix<real>, 2> bilinear_at_samples(const ScaleFactor& chi)
+	// q1[m][k] = q_m(x_k) sqrt(s_k x_k) -- for any number of scale factors in ONE device batch (qb_poly_eval_batch: fma Horner
+	// and the final product on the GPU; the square roots, 2 (D + 1) per constraint, stay on the host)
+	// host half of that batch, one scale factor at a time (thread-safe: run on the host pool): the sample points and the
+	// two square roots per point
+	BilinearSamples prepare_bilinear_samples(const ScaleFactor& chi)
 	{
-		const uint32_t deg = chi.max_degree(), d0 = deg / 2, d1 = deg == 0 ? 0 : (deg - 1) / 2;
-		Matrix<real> q0(d0 + 1, deg + 1), q1(d1 + 1, deg + 1);
-		const auto xs = chi.sample_points();
+		BilinearSamples in;
+		in.xs = chi.sample_points();
 		const auto scs = chi.sample_scalings();
-		const auto q = chi.bilinear_bases();
-		for (uint32_t k = 0; k <= deg; ++k)
+		in.s0 = Vector<real>(in.xs.size());
+		in.s1 = Vector<real>(in.xs.size());
+		for (uint32_t k = 0; k < in.xs.size(); ++k)
 		{
-			const real s0 = mp::sqrt(scs[k]), s1 = mp::sqrt(scs[k] * xs[k]);
-			for (uint32_t m = 0; m <= d0; ++m) q0.at(m, k) = q[m].eval(xs[k]) * s0;
-			for (uint32_t m = 0; m <= d1; ++m) q1.at(m, k) = q[m].eval(xs[k]) * s1;
+			in.s0[k] = mp::sqrt(scs[k]);
+			in.s1[k] = mp::sqrt(scs[k] * in.xs[k]);
 		}
-		return {move(q0), move(q1)};
+		return in;
+	}
+	static vector<std::array<Matrix<real>, 2>> bilinear_at_samples_batch(b200::Engine& eng, const vector<const ScaleFactor*>& chis,
+	                                                                    const vector<const BilinearSamples*>& samples)
+	{
+		const size_t W = size_t(eng.words);
+		vector<int32_t> ofs{0};
+		vector<uint32_t> coef, xr, sr;
+		vector<qb_eval_item> items;
+		auto put = [W](vector<uint32_t>& v, const real& r) { v.insert(v.end(), r._words(), r._words() + W); };
+		for (size_t ci = 0; ci < chis.size(); ++ci)
+		{
+			const ScaleFactor* chi = chis[ci];
+			const BilinearSamples& in = *samples[ci];
+			const uint32_t deg = chi->max_degree(), d0 = deg / 2, d1 = deg == 0 ? 0 : (deg - 1) / 2;
+			const auto q = chi->bilinear_bases();
+			const int32_t pb = int32_t(ofs.size()) - 1, xb = int32_t(xr.size() / W), sb = int32_t(sr.size() / W);
+			for (uint32_t m = 0; m <= d0; ++m)
+			{
+				for (int32_t p = 0; p <= q[m].degree(); ++p) put(coef, q[m].at(uint32_t(p)));
+				ofs.push_back(int32_t(coef.size() / W));
+			}
+			for (uint32_t k = 0; k <= deg; ++k)
+			{
+				put(xr, in.xs[k]);
+				put(sr, in.s0[k]);
+				put(sr, in.s1[k]);
+			}
+			for (uint32_t m = 0; m <= d0; ++m)
+				for (uint32_t k = 0; k <= deg; ++k) items.push_back(qb_eval_item{pb + int32_t(m), xb + int32_t(k), sb + 2 * int32_t(k)});
+			for (uint32_t m = 0; m <= d1; ++m)
+				for (uint32_t k = 0; k <= deg; ++k) items.push_back(qb_eval_item{pb + int32_t(m), xb + int32_t(k), sb + 2 * int32_t(k) + 1});
+		}
+		vector<uint32_t> out(W * items.size());
+		if (!items.empty())
+		{
+			std::lock_guard<std::recursive_mutex> g(eng.mu);
+			eng.check(qb_poly_eval_batch(eng.h, int(ofs.size()) - 1, ofs.data(), coef.data(), int(xr.size() / W), xr.data(), int(sr.size() / W),
+			                             sr.data(), int(items.size()), items.data(), out.data()),
+			          "qb_poly_eval_batch");
+		}
+		vector<std::array<Matrix<real>, 2>> res;
+		res.reserve(chis.size());
+		size_t pos = 0;
+		for (const ScaleFactor* chi : chis)
+		{
+			const uint32_t deg = chi->max_degree(), d0 = deg / 2, d1 = deg == 0 ? 0 : (deg - 1) / 2;
+			Matrix<real> q0(d0 + 1, deg + 1), q1(d1 + 1, deg + 1);
+			for (uint32_t m = 0; m <= d0; ++m)
+				for (uint32_t k = 0; k <= deg; ++k, ++pos) std::memcpy(q0.at(m, k)._words(), out.data() + W * pos, 4 * W);
+			for (uint32_t m = 0; m <= d1; ++m)
+				for (uint32_t k = 0; k <= deg; ++k, ++pos) std::memcpy(q1.at(m, k)._words(), out.data() + W * pos, 4 * W);
+			res.push_back({move(q0), move(q1)});
+		}
+		return res;
 	}
 	// src/polynomial_program.cpp:152-232 -- the per-inequality loops run as ONE pack kernel over all blocks
 	SDPBInput PolynomialProgram::create_input(uint32_t parallel, const unique_ptr<_event_base>& event) &&
@@ -675,16 +755,37 @@ namespace qboot
 			eng->check(qb_pmp_pack(eng->h, int(J), sel.data(), int(eq_sz), lead.data(), int(M), free_idx.data(), eqn.data(), eqt.data()), "qb_pmp_pack");
 			packed->pack_epoch = ++eng->pack_epoch;
 		}
-		// bilinear bases at the sample points, on host threads
+		// bilinear bases at the sample points: convert has evaluated them for the constraints it built; the others (inequalities
+		// from host data) go through one device batch now
+		{
+			vector<const ScaleFactor*> chis;
+			vector<uint32_t> which;
+			for (uint32_t j = 0; j < J; ++j)
+				if (!inequality_[j]->bilinear_)
+				{
+					chis.push_back(inequality_[j]->chi_.get());
+					which.push_back(j);
+				}
+			vector<BilinearSamples> prepared(chis.size());
+			vector<std::function<int()>> prep;
+			for (size_t i = 0; i < chis.size(); ++i)
+				prep.emplace_back([&prepared, &chis, i] {
+					prepared[i] = prepare_bilinear_samples(*chis[i]);
+					return 0;
+				});
+			_parallel_evaluate(prep, parallel);
+			vector<const BilinearSamples*> smp;
+			for (const auto& x : prepared) smp.push_back(&x);
+			auto bl = bilinear_at_samples_batch(*eng, chis, smp);
+			for (size_t i = 0; i < which.size(); ++i) inequality_[which[i]]->bilinear_ = move(bl[i]);
+		}
 		vector<std::function<int()>> tasks;
 		for (uint32_t j = 0; j < J; ++j)
 			tasks.emplace_back([this, &sdpb, &packed, j, M, &event] {
 				_scoped_event scope(std::to_string(j), event);
 				auto& ineq = inequality_[j].value();
 				const uint32_t sz = ineq.size(), deg = ineq.max_degree();
-				// (convert already computed them underneath the GPU phase for the constraints it built)
-				auto bl = ineq.bilinear_ ? move(*ineq.bilinear_) : bilinear_at_samples(*ineq.chi_);
-				sdpb.register_constraint(j, DualConstraint(sz, deg, packed, int32_t(j), int32_t(M), move(bl)));
+				sdpb.register_constraint(j, DualConstraint(sz, deg, packed, int32_t(j), int32_t(M), move(*ineq.bilinear_)));
 				inequality_[j].reset();
 				return 0;
 			});
@@ -905,16 +1006,17 @@ namespace qboot
 			for (uint32_t i = 0; i < J; ++i)
 				for (const auto& m : constraints_[i]->bilinear()) append_records(recs, m, W);
 			std::string text;
-			b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, text);
+			vector<size_t> ends;
+			b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, text, &ends);
 			std::string out = std::to_string(J) + "\n";
 			out.reserve(text.size() + 64 * J);
-			size_t pos = 0;
+			size_t pos = 0, num = 0;
 			for (uint32_t i = 0; i < J; ++i)
 				for (const auto& m : constraints_[i]->bilinear())
 				{
 					out += std::to_string(m.row()) + " " + std::to_string(m.column()) + "\n";
-					size_t cnt = size_t(m.row()) * m.column(), end = pos;
-					for (size_t k = 0; k < cnt; ++k) end = text.find('\n', end) + 1;
+					num += size_t(m.row()) * m.column();
+					const size_t end = num ? ends[num - 1] : 0;
 					out.append(text, pos, end - pos);
 					pos = end;
 				}

@@ -58,6 +58,7 @@ namespace
 		virtual int text_fetch(char*) = 0;
 		virtual int info(int64_t*) = 0;
 		virtual int dec_format(int, int, const uint32_t*, char*, int, int32_t*) = 0;
+		virtual int poly_eval(int, const int32_t*, const uint32_t*, int, const uint32_t*, int, const uint32_t*, int, const qb_eval_item*, uint32_t*) = 0;
 	};
 	template <int L>
 	struct Emu : EmuBase
@@ -324,6 +325,21 @@ namespace
 			tb.ndigits = ndigits;
 			return 0;
 		}
+		int poly_eval(int n_polys, const int32_t* ofs, const uint32_t* coef, int n_x, const uint32_t* x, int n_s, const uint32_t* s, int n_items,
+		              const qb_eval_item* items, uint32_t* out) override
+		{
+			(void)n_polys;
+			(void)n_x;
+			(void)n_s;
+			const T* c = reinterpret_cast<const T*>(coef);
+			for (int i = 0; i < n_items; ++i)
+			{
+				const int o = ofs[items[i].poly], deg = ofs[items[i].poly + 1] - o - 1;
+				poly_eval_scaled<L>(reinterpret_cast<T*>(out)[i], c + o, deg, reinterpret_cast<const T*>(x)[items[i].x],
+				                    reinterpret_cast<const T*>(s)[items[i].s], prec);
+			}
+			return 0;
+		}
 		int dec_format(int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* l) override
 		{
 			if (int rc = prepare(ndigits)) return rc;
@@ -489,5 +505,10 @@ extern "C"
 	int qb_dec_format(qb_handle* h, int ndigits, int n, const uint32_t* x, char* slots, int slot, int32_t* len)
 	{
 		return h->e->dec_format(ndigits, n, x, slots, slot, len);
+	}
+	int qb_poly_eval_batch(qb_handle* h, int n_polys, const int32_t* poly_ofs, const uint32_t* coef, int n_x, const uint32_t* x, int n_s,
+	                       const uint32_t* s, int n_items, const qb_eval_item* items, uint32_t* out)
+	{
+		return h->e->poly_eval(n_polys, poly_ofs, coef, n_x, x, n_s, s, n_items, items, out);
 	}
 }
