@@ -225,6 +225,73 @@ def test_chunked_streams_match_single_chunk(tmp_path):
     assert np.array_equal(out["g2"], want)
 
 
+def test_sink_receives_the_tables_of_every_run():
+    """qb_gblock_set_sink: every finished chunk of a run is copied to the sink (here page-locked host memory; in a multi-GPU
+    job a peer GPU's buffer opened with qb_ipc_open) and the handle's stream joins the copies"""
+    import ctypes as C
+
+    prec, n_max, lam, n = 600, 60, 9, 700
+    rng = random.Random(5)
+    spin, delta, S, P = _random_inputs(rng, prec, n)
+    eng = _engine(prec, n_max, lam)
+    nbytes = n * eng.dim_M * eng.W * 4
+    buf = eng.lib.qb_pinned_alloc(nbytes)
+    assert buf
+    try:
+        view = np.frombuffer((C.c_ubyte * nbytes).from_address(buf), dtype=np.uint32).reshape(n, eng.dim_M, eng.W)
+        view[:] = 0
+        eng._check(eng.lib.qb_gblock_set_sink(eng.h, buf), "qb_gblock_set_sink")
+        eng.plan(spin, delta, S, P)
+        eng.run()
+        eng.sync()
+        want = eng.fetch()
+        assert np.array_equal(view, want)
+        # switched off: a later run leaves the buffer alone
+        eng._check(eng.lib.qb_gblock_set_sink(eng.h, None), "qb_gblock_set_sink")
+        view[:] = 0
+        eng.run()
+        eng.sync()
+        assert not view.any()
+    finally:
+        eng.lib.qb_gblock_set_sink(eng.h, None)
+        eng.close()
+        eng.lib.qb_pinned_free(buf)
+
+
+def test_poly_eval_batch_vs_reference(ref):
+    """qb_poly_eval_batch -- the bilinear bases at the sample points: Horner by fused multiply-adds (Polynomial::eval with a
+    real argument, polynomial.hpp:66-83) times a scale -- against mpfr_fma / mpfr_mul chains"""
+    import ctypes as C
+
+    from tests.golden.make_golden import rnd_num
+    from tests.util import P
+
+    prec = 1000
+    eng = _engine(prec, 20, 5)
+    rng = random.Random(77)
+    degs = [-1, 0, 1, 2, 5, 13, 24]                      # -1: the zero polynomial
+    coefs = [[rnd_num(rng, prec, -8, 8) for _ in range(d + 1)] for d in degs]
+    ofs = np.cumsum([0] + [d + 1 for d in degs]).astype(np.int32)
+    flat = np.stack([c for cs in coefs for c in cs])
+    xs = np.stack([rnd_num(rng, prec, -2, 6) for _ in range(9)])
+    ss = np.stack([rnd_num(rng, prec, -3, 3) for _ in range(4)])
+    items = np.array([(p, x, s) for p in range(len(degs)) for x in range(len(xs)) for s in range(len(ss))], dtype=np.int32)
+    out = np.zeros((len(items), eng.W), dtype=np.uint32)
+    eng._check(eng.lib.qb_poly_eval_batch(eng.h, len(degs), P(ofs), P(flat), len(xs), P(xs), len(ss), P(ss), len(items), P(items), P(out)),
+               "qb_poly_eval_batch")
+    zero = qb.from_fraction(0, prec)
+    for i, (p, x, s) in enumerate(items):
+        if degs[p] < 0:
+            acc = zero
+        else:
+            acc = coefs[p][degs[p]]
+            for k in range(degs[p] - 1, -1, -1):
+                acc = ref.op("fma", prec, a=acc, b=xs[x], c=coefs[p][k])[0]
+        want = ref.op("mul", prec, a=acc, b=ss[s])[0]
+        assert same_records(want[None, :], out[i][None, :]), (p, x, s)
+    eng.close()
+
+
 def test_bench_workload_vs_reference(ref):
     """The benchmark's own workload (mixed-Ising key set at lambda = 19, n_Max = 400, 1024-bit, full-width sample points)
     sampled across spins and (S, P) classes, against the reference run on this box: what bench.py times is what is pinned."""
