@@ -151,6 +151,7 @@ namespace qb
 		DevBuf d_ziv;  // two counters of the powers' Ziv loop
 		int ziv_slack = QB_ZIV_SLACK;
 		uint64_t ziv_reported = 0;
+		DevBuf d_b0tab;  // b[0] by spin (src/hor_recursion.cpp:17-19)
 		DevBuf d_coefx;  // fixed-point copy of the recurrence coefficients (polyfx.cuh)
 		DevBuf d_consts, d_in, d_jobs, d_coef, d_b, d_fr, d_g, d_tref, d_pw, d_qc, d_a, d_fb_in, d_fb_v, d_fb_out, d_fb_terms, d_fb_g;
 		DevCtx cx{};
@@ -159,7 +160,7 @@ namespace qb
 		// layout of d_in: [delta | S | P] (tables) then spin; d_jobs: [delta | S | P | b0] (jobs) then spin
 		T *t_delta = nullptr, *t_S = nullptr, *t_P = nullptr;
 		uint32_t* t_spin = nullptr;
-		T *j_delta = nullptr, *j_S = nullptr, *j_P = nullptr, *j_b0 = nullptr;
+		T *j_delta = nullptr, *j_S = nullptr, *j_P = nullptr;  // per job; alias the table arrays when no operator is divergent
 		uint32_t* j_spin = nullptr;
 		std::vector<cudaEvent_t> ev;    // timing: one in front of every stage (tick)
 		std::vector<int> ev_stage;      // stage that follows ev[i], -1 none
@@ -183,7 +184,7 @@ namespace qb
 		~Engine() override
 		{
 			cudaSetDevice(device);
-			for (DevBuf* b : {&d_ziv, &d_coefx, &d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_qc, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
+			for (DevBuf* b : {&d_ziv, &d_b0tab, &d_coefx, &d_consts, &d_in, &d_jobs, &d_coef, &d_b, &d_fr, &d_g, &d_tref, &d_pw, &d_qc, &d_a, &d_fb_in, &d_fb_v, &d_fb_out,
 			                  &d_fb_terms, &d_fb_g})
 				b->release();
 			pmp_release();
@@ -395,26 +396,36 @@ namespace qb
 			const T* hd = reinterpret_cast<const T*>(delta);
 			const T* hS = reinterpret_cast<const T*>(S);
 			const T* hP = reinterpret_cast<const T*>(P);
-			std::vector<T> jd, jS, jP, jb;
+			std::vector<T> jd, jS, jP;
 			std::vector<uint32_t> jsp;
 			std::vector<TableRef> tr(static_cast<size_t>(n));
-			jd.reserve(size_t(n));
-			jS.reserve(size_t(n));
-			jP.reserve(size_t(n));
-			jb.reserve(size_t(n));
-			jsp.reserve(size_t(n));
 			T small, onep, onem;
 			set_ui_2exp(small, 1, -(3 * prec) / 8 + 15, prec);  // 2^(-(3 prec)/8 + 15)          (hor_recursion.cpp:23)
 			add_si(onep, small, 1, prec);
 			neg(small);
 			add_si(onem, small, 1, prec);
+			uint32_t max_spin = 0;
 			for (int t = 0; t < n; ++t)
 			{
 				if ((hd[t].sk & 2u) || (hS[t].sk & 2u) || (hP[t].sk & 2u)) return -4;  // inf / nan
 				if (spin[t] > 400) return -6;
+				max_spin = std::max(max_spin, spin[t]);
+			}
+			// b[0] depends on the spin only: a table indexed by spin (401 records at most) instead of a record per job
+			std::vector<T> b0tab(size_t(max_spin) + 1);
+			{
+				std::vector<uint8_t> seen(size_t(max_spin) + 1, 0);
+				for (auto& x : b0tab) set_zero(x);
+				for (int t = 0; t < n; ++t)
+					if (!seen[spin[t]])
+					{
+						seen[spin[t]] = 1;
+						if (int rc = leading_coefficient(b0tab[spin[t]], spin[t])) return rc;
+					}
 			}
 			// the divergence test is the only per-table arithmetic of the planner: fan it out over host threads
 			std::vector<uint8_t> diverges(static_cast<size_t>(n), 0);
+			bool any_divergent = false;
 			{
 				const int nth = n >= 4096 ? int(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
 				auto work = [&](int lo, int hi) {
@@ -424,40 +435,47 @@ namespace qb
 				for (int k = 1; k < nth; ++k) pool.emplace_back(work, int(int64_t(n) * k / nth), int(int64_t(n) * (k + 1) / nth));
 				work(0, int(int64_t(n) / nth));
 				for (auto& th : pool) th.join();
+				for (int t = 0; t < n && !any_divergent; ++t) any_divergent = diverges[size_t(t)] != 0;
 			}
-			for (int t = 0; t < n; ++t)
+			// Common case, no divergent operator: job t IS table t -- the device-side job arrays alias the table arrays and
+			// nothing is repacked (for a scan-sized batch the repacking and its upload were ~0.1 s of host time per call).
+			if (!any_divergent)
+				for (int t = 0; t < n; ++t) tr[size_t(t)] = TableRef{t, -1};
+			else
 			{
-				if ((hd[t].sk & 2u) || (hS[t].sk & 2u) || (hP[t].sk & 2u)) return -4;
-				T b0;
-				int rc = leading_coefficient(b0, spin[t]);
-				if (rc) return rc;
-				auto push = [&](const T& D) {
-					jd.push_back(D);
-					jS.push_back(hS[t]);
-					jP.push_back(hP[t]);
-					jb.push_back(b0);
-					jsp.push_back(spin[t]);
-					return int32_t(jd.size() - 1);
-				};
-				if (diverges[size_t(t)])
+				jd.reserve(size_t(n));
+				jS.reserve(size_t(n));
+				jP.reserve(size_t(n));
+				jsp.reserve(size_t(n));
+				for (int t = 0; t < n; ++t)
 				{
-					// two evaluations at Delta (1 +- s), averaged                         (primary_op.hpp:53-56)
-					T dp, dm;
-					mul(dp, hd[t], onep, prec);
-					mul(dm, hd[t], onem, prec);
-					tr[size_t(t)].job0 = push(dp);
-					tr[size_t(t)].job1 = push(dm);
-				}
-				else
-				{
-					tr[size_t(t)].job0 = push(hd[t]);
-					tr[size_t(t)].job1 = -1;
+					auto push = [&](const T& D) {
+						jd.push_back(D);
+						jS.push_back(hS[t]);
+						jP.push_back(hP[t]);
+						jsp.push_back(spin[t]);
+						return int32_t(jd.size() - 1);
+					};
+					if (diverges[size_t(t)])
+					{
+						// two evaluations at Delta (1 +- s), averaged                         (primary_op.hpp:53-56)
+						T dp, dm;
+						mul(dp, hd[t], onep, prec);
+						mul(dm, hd[t], onem, prec);
+						tr[size_t(t)].job0 = push(dp);
+						tr[size_t(t)].job1 = push(dm);
+					}
+					else
+					{
+						tr[size_t(t)].job0 = push(hd[t]);
+						tr[size_t(t)].job1 = -1;
+					}
 				}
 			}
 			// from here on the previous plan is gone; the new one counts only once everything below has succeeded
 			n_tables = 0;
 			tables_valid = false;
-			n_jobs = int(jd.size());
+			n_jobs = any_divergent ? int(jd.size()) : n;
 			job_of_table.assign(size_t(n) + 1, n_jobs);
 			for (int t = 0; t < n; ++t) job_of_table[size_t(t)] = tr[size_t(t)].job0;
 			// Chunks of CHUNK tables (the last one shorter); the scaled-coefficient scratch is one chunk-sized slot.
@@ -495,7 +513,8 @@ namespace qb
 			a_slot_records = (size_t(lambda) + 1) * (size_t(n_max) + 1) * size_t(n_chunks > 1 ? max_chunk : n);
 			if (n == 0) return 0;
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
-			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || d_jobs.ensure(sizeof(T) * 4 * nj + 4 * nj) ||
+			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || (any_divergent && d_jobs.ensure(sizeof(T) * 3 * nj + 4 * nj)) ||
+			    d_b0tab.ensure(sizeof(T) * b0tab.size()) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
 			    d_coefx.ensure(4 * size_t(fx_words<L>()) * QB_NCOEF * nj) ||
 			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (2 * n1 + 1) * nt) || d_qc.ensure(sizeof(T) * nt) || d_a.ensure(sizeof(T) * a_slot_records) ||
@@ -505,20 +524,29 @@ namespace qb
 			t_S = t_delta + nt;
 			t_P = t_S + nt;
 			t_spin = reinterpret_cast<uint32_t*>(t_P + nt);
-			j_delta = d_jobs.as<T>();
-			j_S = j_delta + nj;
-			j_P = j_S + nj;
-			j_b0 = j_P + nj;
-			j_spin = reinterpret_cast<uint32_t*>(j_b0 + nj);
 			QB_CU(cudaMemcpyAsync(t_delta, hd, sizeof(T) * nt, cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaMemcpyAsync(t_S, hS, sizeof(T) * nt, cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaMemcpyAsync(t_P, hP, sizeof(T) * nt, cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaMemcpyAsync(t_spin, spin, 4 * nt, cudaMemcpyHostToDevice, stream));
-			QB_CU(cudaMemcpyAsync(j_delta, jd.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
-			QB_CU(cudaMemcpyAsync(j_S, jS.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
-			QB_CU(cudaMemcpyAsync(j_P, jP.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
-			QB_CU(cudaMemcpyAsync(j_b0, jb.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
-			QB_CU(cudaMemcpyAsync(j_spin, jsp.data(), 4 * nj, cudaMemcpyHostToDevice, stream));
+			if (any_divergent)
+			{
+				j_delta = d_jobs.as<T>();
+				j_S = j_delta + nj;
+				j_P = j_S + nj;
+				j_spin = reinterpret_cast<uint32_t*>(j_P + nj);
+				QB_CU(cudaMemcpyAsync(j_delta, jd.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
+				QB_CU(cudaMemcpyAsync(j_S, jS.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
+				QB_CU(cudaMemcpyAsync(j_P, jP.data(), sizeof(T) * nj, cudaMemcpyHostToDevice, stream));
+				QB_CU(cudaMemcpyAsync(j_spin, jsp.data(), 4 * nj, cudaMemcpyHostToDevice, stream));
+			}
+			else
+			{
+				j_delta = t_delta;
+				j_S = t_S;
+				j_P = t_P;
+				j_spin = t_spin;
+			}
+			QB_CU(cudaMemcpyAsync(d_b0tab.p, b0tab.data(), sizeof(T) * b0tab.size(), cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaMemcpyAsync(d_tref.p, tr.data(), sizeof(TableRef) * nt, cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaStreamSynchronize(stream));  // host vectors go out of scope
 			n_tables = n;
@@ -545,7 +573,7 @@ namespace qb
 		}
 		void stage_series(const Range& r, cudaStream_t st)
 		{
-			launch_series<L>(cx, r.j1 - r.j0, j_delta + r.j0, j_spin + r.j0, j_b0 + r.j0, d_coef.as<T>() + size_t(r.j0) * QB_NCOEF,
+			launch_series<L>(cx, r.j1 - r.j0, j_delta + r.j0, j_spin + r.j0, d_b0tab.as<T>(), d_coef.as<T>() + size_t(r.j0) * QB_NCOEF,
 			                 d_coefx.as<uint32_t>() + size_t(r.j0) * QB_NCOEF * fx_words<L>(), d_b.as<T>() + size_t(r.j0) * (size_t(n_max) + 1), st);
 			++launches;
 		}

@@ -141,7 +141,7 @@ namespace qb
 		mpf<L>* bj = b + size_t(active ? job : 0) * (n_max + 1);
 		if (active)
 		{
-			copy(bj[0], b0[job]);
+			copy(bj[0], b0[spin[job]]);  // b[0] by spin (a table of at most 401 records)
 			if (is_zero(delta[job]))
 			{
 				// unit operator: b = (b0, 0, 0, ...)                                  (src/hor_recursion.cpp:20)
