@@ -239,22 +239,24 @@ namespace qb
 						}
 					}
 				}
+				// p_i(n) goes to its shared-memory slot at once: only its sign / kind word and exponent stay in registers
+				series_store<L, T>(myp, psk, pexp, p);
 				if (divisor)
 				{
 					// b[n] = -sum / p_0(n)
-					mpf<L> sum, bn;
+					mpf<L> sum, bn, p0;
 					series_load<L, T>(sum, mys, ssk, sexp);
+					series_load<L, T>(p0, myp, psk, pexp);
 					neg(sum);
-					fast::div(bn, sum, p, prec);
+					fast::div(bn, sum, p0, prec);
 					copy(bj[n], bn);
 					continue;
 				}
 				mpf<L> bp;
 				ldg_rec64(bp, &bj[n - uint32_t(i)]);
 				bool done = false;
-				if ((p.sk & 3u) == K_REG && (bp.sk & 3u) == K_REG && (i == 1 || (ssk & 3u) == K_REG))
+				if ((psk & 3u) == K_REG && (bp.sk & 3u) == K_REG && (i == 1 || (ssk & 3u) == K_REG))
 				{
-					series_store<L, T>(myp, psk, pexp, p);
 					uint32_t X[L + 3], stt;
 					int32_t e;
 					fast::product_frame<L, T>(X, stt, e, myp, pexp, bp);
@@ -273,13 +275,15 @@ namespace qb
 				if (!done)
 				{
 					// special values, deep cancellation: the generic routines (same correctly rounded result)
-					mpf<L> sum, r;
+					mpf<L> sum, r, pp, bb;
+					series_load<L, T>(pp, myp, psk, pexp);
+					ldg_rec64(bb, &bj[n - uint32_t(i)]);
 					if (i == 1)
-						fast::cold_mul(r, p, bp, prec);
+						fast::cold_mul(r, pp, bb, prec);
 					else
 					{
 						series_load<L, T>(sum, mys, ssk, sexp);
-						fast::cold_fma(r, p, bp, sum, prec);
+						fast::cold_fma(r, pp, bb, sum, prec);
 					}
 					series_store<L, T>(mys, ssk, sexp, r);
 				}

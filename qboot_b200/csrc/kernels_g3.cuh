@@ -48,9 +48,15 @@ namespace qb
 		}
 	}
 
-	constexpr int QB_OFFDIAG_THREADS = 256;
+#ifndef QB_OFFDIAG_T
+#define QB_OFFDIAG_T 128
+#endif
+#ifndef QB_OFFDIAG_CTAS
+#define QB_OFFDIAG_CTAS 4
+#endif
+	constexpr int QB_OFFDIAG_THREADS = QB_OFFDIAG_T;
 	template <int L>
-	__global__ void __launch_bounds__(QB_OFFDIAG_THREADS, 2) k_offdiag_val(DevCtx cx, int n_tables, int n, const mpf<L>* __restrict__ S,
+	__global__ void __launch_bounds__(QB_OFFDIAG_THREADS, QB_OFFDIAG_CTAS) k_offdiag_val(DevCtx cx, int n_tables, int n, const mpf<L>* __restrict__ S,
 	                                                                    const mpf<L>* __restrict__ P, const mpf<L>* __restrict__ qc, mpf<L>* g)
 	{
 		const int lambda = int(cx.lambda), dimM = cf_dim(lambda), cnt = lambda - 2 * n + 1;
