@@ -90,7 +90,7 @@ namespace qb
 		const int threads = 128, lambda = int(cx.lambda);
 		auto blocks = [&](int64_t total) { return unsigned((total + threads - 1) / threads); };
 		int count = 1;
-		k_rho_to_z<QB_L><<<blocks(int64_t(n_tables) * (lambda + 1)), threads, 0, st>>>(cx, n_tables, delta, spin, fr, g, qc);
+		k_rho_to_z<QB_L><<<blocks(int64_t(n_tables) * ((lambda + 2) / 2)), threads, 0, st>>>(cx, n_tables, delta, spin, fr, g, qc);
 		for (int n = 1; n <= lambda / 2; ++n)
 		{
 			k_offdiag_val<QB_L><<<unsigned((int64_t(n_tables) * (lambda - 2 * n + 1) + QB_OFFDIAG_THREADS - 1) / QB_OFFDIAG_THREADS), QB_OFFDIAG_THREADS, 0, st>>>(

@@ -20,25 +20,33 @@
 namespace qb
 {
 	// Stage a5 + a6 as a short sequence of WIDE kernels (every lane does the same amount of work):
-	//   k_rho_to_z        thread per (table, i): entry i of the rho -> z matrix-vector product (a dot product of lambda + 1
-	//                     terms, matrix.hpp:444-456); the i == 0 thread also leaves 4 C_2 of the table in qc[table]
+	//   k_rho_to_z        thread per (table, column pair i / lambda - i): entries of the rho -> z matrix-vector product (dot
+	//                     products of lambda + 1 terms, matrix.hpp:444-456); the i == 0 thread also leaves 4 C_2 of the table in qc[table]
 	//   k_offdiag_val     per dy-level n, thread per (table, dx = m): the part of the Casimir recursion that only reads
 	//                     levels n - 1 and n - 2 (context.cpp:72-121) -> written into the table slot (m, n)
 	//   k_offdiag_close   per dy-level n, thread per table: the same-level correction, sequential in m (context.cpp:122-131)
 	// lambda / 2 levels => 1 + 2 * (lambda / 2) launches per chunk; the kernel boundary is the level barrier.
+	// (thread per (table, pair of columns): column i and column lambda - i of the triangular matrix together cost lambda + 2
+	// products whatever i is, so the lanes of a warp finish together -- one thread per column left 22 of 32 lanes idle)
 	template <int L>
 	__global__ void __launch_bounds__(128) k_rho_to_z(DevCtx cx, int n_tables, const mpf<L>* __restrict__ delta,
 	                                                  const uint32_t* __restrict__ spin, const mpf<L>* __restrict__ fr,
 	                                                  mpf<L>* __restrict__ g, mpf<L>* __restrict__ qc)
 	{
-		const int lambda = int(cx.lambda), nk = lambda + 1, dimM = cf_dim(lambda), prec = cx.prec;
+		const int lambda = int(cx.lambda), nk = lambda + 1, np = (nk + 1) / 2, dimM = cf_dim(lambda), prec = cx.prec;
 		const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-		const int t = gid / nk, i = gid - t * nk;
+		const int t = gid / np, i = gid - t * np;
 		if (t >= n_tables) return;
 		const mpf<L>* M = reinterpret_cast<const mpf<L>*>(cx.mat);
-		mpf<L> z;
-		rho_to_z_entry(z, fr + size_t(t) * nk, 1, M, lambda, i, prec);
-		copy(g[size_t(t) * dimM + i], z);
+		QB_ROLL
+		for (int w = 0; w < 2; ++w)
+		{
+			const int col = w == 0 ? i : lambda - i;
+			if (w == 1 && col == i) break;
+			mpf<L> z;
+			rho_to_z_entry(z, fr + size_t(t) * nk, 1, M, lambda, col, prec);
+			copy(g[size_t(t) * dimM + col], z);
+		}
 		if (i == 0)
 		{
 			mpf<L> lD, q4;
