@@ -295,23 +295,38 @@ def main():
     if world > 1 and gather_mode == "peer":
         import ctypes as C
 
+        # every rank must be able to map rank 0's buffer (CUDA IPC + peer access); if any cannot, all fall back to the collective
+        ok = 1
         handle = torch.zeros(64, dtype=torch.uint8, device=f"cuda:{local}")
         if rank == 0:
             sink_base = eng.lib.qb_device_alloc(eng.h, world * shard_bytes)
-            if not sink_base:
-                raise SystemExit("qb_device_alloc failed")
             hb = (C.c_ubyte * 64)()
-            eng._check(eng.lib.qb_ipc_export(eng.h, sink_base, hb), "qb_ipc_export")
-            handle.copy_(torch.tensor(list(hb), dtype=torch.uint8))
+            if not sink_base or eng.lib.qb_ipc_export(eng.h, sink_base, hb) != 0:
+                ok = 0
+            else:
+                handle.copy_(torch.tensor(list(hb), dtype=torch.uint8))
         dist.broadcast(handle, src=0)
         if rank != 0:
             hb = (C.c_ubyte * 64)(*handle.cpu().tolist())
             ptr = C.c_void_p()
-            eng._check(eng.lib.qb_ipc_open(eng.h, hb, C.byref(ptr)), "qb_ipc_open")
-            sink_base = ptr.value
-        sink_local = sink_base + rank * shard_bytes
-        eng._check(eng.lib.qb_gblock_set_sink(eng.h, sink_local), "qb_gblock_set_sink")
-    elif world > 1:
+            if eng.lib.qb_ipc_open(eng.h, hb, C.byref(ptr)) != 0 or not ptr.value:
+                ok = 0
+            else:
+                sink_base = ptr.value
+        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{local}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag[0]) == 0:
+            if sink_base and rank != 0:
+                eng.lib.qb_ipc_close(eng.h, sink_base)
+            dist.barrier()
+            if sink_base and rank == 0:
+                eng.lib.qb_device_free(eng.h, sink_base)
+            sink_base = None
+            gather_mode = "nccl"
+        else:
+            sink_local = sink_base + rank * shard_bytes
+            eng._check(eng.lib.qb_gblock_set_sink(eng.h, sink_local), "qb_gblock_set_sink")
+    if world > 1 and gather_mode != "peer":
         mine = torch.as_tensor(_DevBytes(eng.lib.qb_gblock_device_tables(eng.h), shard_bytes), device=f"cuda:{local}")
         gathered = [torch.empty(shard_bytes, dtype=torch.uint8, device=f"cuda:{local}") for _ in range(world)] if rank == 0 else None
 
