@@ -999,19 +999,19 @@ namespace qboot
 			write_file(root / "blocks.0", out.str(), nullptr, 0);
 			return 0;
 		});
-		tasks.emplace_back([&] {
-			_scoped_event scope("write_bilinear_bases", event);
-			// all numbers of the file in one device batch, then interleave the "rows cols" headers
-			vector<uint32_t> recs;
-			for (uint32_t i = 0; i < J; ++i)
+		// bilinear_bases.0: one piece of text per constraint ("rows cols" headers + numbers), formatted by the host pool in
+		// parallel (the device formats each piece's numbers) and written out back to back afterwards
+		vector<std::string> bl_pieces(J);
+		for (uint32_t i = 0; i < J; ++i)
+			tasks.emplace_back([&, i] {
+				vector<uint32_t> recs;
 				for (const auto& m : constraints_[i]->bilinear()) append_records(recs, m, W);
-			std::string text;
-			vector<size_t> ends;
-			b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, text, &ends);
-			std::string out = std::to_string(J) + "\n";
-			out.reserve(text.size() + 64 * J);
-			size_t pos = 0, num = 0;
-			for (uint32_t i = 0; i < J; ++i)
+				std::string text;
+				vector<size_t> ends;
+				b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, text, &ends);
+				std::string& out = bl_pieces[i];
+				out.reserve(text.size() + 64);
+				size_t pos = 0, num = 0;
 				for (const auto& m : constraints_[i]->bilinear())
 				{
 					out += std::to_string(m.row()) + " " + std::to_string(m.column()) + "\n";
@@ -1020,9 +1020,8 @@ namespace qboot
 					out.append(text, pos, end - pos);
 					pos = end;
 				}
-			write_file(root / "bilinear_bases.0", out, nullptr, 0);
-			return 0;
-		});
+				return 0;
+			});
 		tasks.emplace_back([&] {
 			_scoped_event scope("write_objectives", event);
 			vector<uint32_t> recs(constant_term_._words(), constant_term_._words() + W);
@@ -1039,6 +1038,15 @@ namespace qboot
 		tasks.clear();
 		if (text_thread.joinable()) text_thread.join();
 		if (text_error) std::rethrow_exception(text_error);
+		tasks.emplace_back([&] {
+			_scoped_event scope("write_bilinear_bases", event);
+			std::ofstream f(root / "bilinear_bases.0", std::ios::binary);
+			const std::string head = std::to_string(J) + "\n";
+			f.write(head.data(), std::streamsize(head.size()));
+			for (const auto& piece : bl_pieces) f.write(piece.data(), std::streamsize(piece.size()));
+			if (!f) throw std::runtime_error("qboot_b200: cannot write " + (root / "bilinear_bases.0").string());
+			return 0;
+		});
 		for (uint32_t i = 0; i < J; ++i)
 			tasks.emplace_back([&, i] {
 				_scoped_event scope("write constraint " + std::to_string(i), event);
