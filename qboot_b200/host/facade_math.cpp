@@ -223,23 +223,24 @@ namespace qboot
 			return algebra::lower_triangular_inverse(algebra::cholesky_decomposition(a));
 		}
 		// int_0^inf base^x x^n dx = n! / (-ln base)^(n+1), n = 0..order   (src/conformal_scale.cpp:20-31)
-		Vector<real> moments_no_pole(uint32_t order, const real& base)
+		// (ln base is the same correctly rounded number wherever it is evaluated: the caller computes it once per scale factor)
+		Vector<real> moments_no_pole(uint32_t order, const real& lnb)
 		{
 			Vector<real> m(order + 1);
-			const real inv = -1 / mp::log(base);
+			const real inv = -1 / lnb;
 			m[0] = inv;
 			for (uint32_t j = 1; j <= order; ++j) m[j] = m[j - 1] * j * inv;
 			return m;
 		}
 		// int_0^inf base^x x^n / (x - pole) dx for n = 0..order, pole <= 0: with E = base^pole Gamma(0, pole ln base),
 		//   m[0] = E,   m[j] = sum_{i < j} (j - i - 1)! pole^i (-1/ln base)^(j - i) + E pole^j      (src/conformal_scale.cpp:33-70)
-		Vector<real> moments_simple_pole(uint32_t order, const real& base, const real& pole)
+		Vector<real> moments_simple_pole(uint32_t order, const real& base, const real& lnb, const real& pole)
 		{
-			const real e = pole == 0 ? real(mp::global_prec) : mp::pow(base, pole) * mp::gamma_inc(real(0), pole * mp::log(base));
+			const real e = pole == 0 ? real(mp::global_prec) : mp::pow(base, pole) * mp::gamma_inc(real(0), pole * lnb);
 			Vector<real> m(order + 1);
 			m[0] = e;
 			real run{}, tail = pole * e, fact(1);
-			const real inv = -1 / mp::log(base);
+			const real inv = -1 / lnb;
 			real inv_pow = inv;
 			for (uint32_t j = 1; j <= order; ++j)
 			{
@@ -295,12 +296,12 @@ namespace qboot
 				if (i > 0 && shifted[i] == shifted[i - 1]) shifted[i] -= tiny;
 		}
 		const Vector<real> weight = partial_fraction_weights(shifted);
-		const real base = 4 * rho_;
+		const real base = 4 * rho_, lnb = mp::log(base);
 		Vector<real> moments(2 * deg + 1);
 		if (np == 0)
-			moments = moments_no_pole(2 * deg, base);
+			moments = moments_no_pole(2 * deg, lnb);
 		else
-			for (uint32_t i = 0; i < np; ++i) moments += mul_scalar(weight[i], moments_simple_pole(2 * deg, base, shifted[i]));
+			for (uint32_t i = 0; i < np; ++i) moments += mul_scalar(weight[i], moments_simple_pole(2 * deg, base, lnb, shifted[i]));
 		moments *= mp::pow(base, gap_);
 		Matrix<real> q = hankel_orthonormalise(moments);
 		for (uint32_t i = 0; i <= deg; ++i)

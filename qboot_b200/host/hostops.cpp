@@ -533,16 +533,35 @@ namespace qb::host
 	}
 	namespace
 	{
+		// ln of the last base, per thread: a scale factor raises the same base (4 rho) to some eighty powers, and the
+		// logarithm is two thirds of a power's cost.  A cached value of higher working precision serves any request of lower
+		// precision -- it only satisfies the error bound better, and the Ziv loop around it makes the rounded result unique.
+		XF cached_log(const XF& ax, int64_t wp)
+		{
+			struct Cache
+			{
+				Nat m;
+				int64_t e = 0, wp = -1;
+				XF value;
+			};
+			thread_local Cache c;
+			if (c.wp >= wp && c.e == ax.e && cmp(c.m, ax.m) == 0) return c.value;
+			c.value = xf_log(ax, wp + 64);
+			c.m = ax.m;
+			c.e = ax.e;
+			c.wp = wp + 64;
+			return c.value;
+		}
 		// |x|^y for regular x != 1 and regular y through exp(y ln|x|)
 		void pow_general(uint32_t* r, const XF& x, const XF& y, bool neg_result, int prec)
 		{
 			XF ax = x;
 			ax.neg = false;
 			ziv(r, prec, [&](int64_t wp) {
-				XF l0 = xf_log(ax, 64);
+				XF l0 = cached_log(ax, 64);
 				if (l0.zero()) return xf_from_int(1);
 				const int64_t tb = std::max<int64_t>(0, l0.top() + y.top()) + 8;  // bits of |y ln x|
-				XF lx = xf_log(ax, wp + tb + 8);
+				XF lx = cached_log(ax, wp + tb + 8);
 				XF t = xf_mul(y, lx, wp + tb + 8);
 				XF v = xf_exp(t, wp);
 				v.neg = neg_result;
