@@ -32,12 +32,39 @@ namespace qboot
 				if (const char* v = std::getenv(name)) return std::atoi(v);
 			return 0;
 		}
+		namespace
+		{
+			// One spare engine handle per (device, precision) outlives the Context that used it: a scan builds one Context per
+			// grid point, and creating a handle means allocating (and, on destruction, freeing) its device arenas -- hundreds
+			// of megabytes, occasionally half a second.  qb_context_init resets everything a previous owner left behind.
+			// The pool is never destroyed (no CUDA calls during static destruction).
+			struct HandlePool
+			{
+				std::mutex mu;
+				std::map<std::pair<int, int>, qb_handle*> spare;
+			};
+			HandlePool& handle_pool()
+			{
+				static HandlePool* p = new HandlePool;
+				return *p;
+			}
+		}  // namespace
 		Engine::Engine(int prec_bits, uint32_t n_max_, uint32_t lambda_, const rational& epsilon)
 		    : prec(prec_bits), device(pick_device()), n_max(n_max_), lambda(lambda_)
 		{
 			qb::host::check_prec(prec);
 			if (epsilon.den() > int64_t(UINT32_MAX)) throw std::overflow_error("qboot_b200: epsilon denominator exceeds 32 bits");
-			int rc = qb_create(device, prec, &h);
+			{
+				HandlePool& pool = handle_pool();
+				std::lock_guard<std::mutex> g(pool.mu);
+				auto it = pool.spare.find({device, prec});
+				if (it != pool.spare.end())
+				{
+					h = it->second;
+					pool.spare.erase(it);
+				}
+			}
+			int rc = h ? QB_OK : qb_create(device, prec, &h);
 			if (rc != QB_OK)
 				throw std::runtime_error(std::string("qboot_b200: cannot create the GPU engine: ") + qb_strerror(rc) +
 				                         " (block tables are computed on a CUDA device; there is no CPU path)");
@@ -56,7 +83,19 @@ namespace qboot
 		}
 		Engine::~Engine()
 		{
-			if (h) qb_destroy(h);
+			if (!h) return;
+			qb_handle* drop = h;
+			{
+				HandlePool& pool = handle_pool();
+				std::lock_guard<std::mutex> g(pool.mu);
+				auto& slot = pool.spare[{device, prec}];
+				if (!slot)
+				{
+					slot = h;
+					drop = nullptr;
+				}
+			}
+			if (drop) qb_destroy(drop);
 		}
 		int Engine::check(int rc, const char* what, bool nonneg_ok) const
 		{
