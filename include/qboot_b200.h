@@ -114,7 +114,7 @@ void qb_pinned_free(void* p);
 
 /* Measurement support.  qb_set_timing(h, 1) brackets each kernel of qb_gblock_run with CUDA events on the handle's
  * stream (chunks then run back to back on that one stream); qb_kernel_times synchronises and returns the device times
- * in ms of the last run: [0] recurrence coefficients, [1] polynomial values + series recurrence, [2] powers +
+ * in ms of the last run: [0] recurrence coefficients (+ their fixed-point copy), [1] series recurrence, [2] powers +
  * rho-derivative chains (scale, Horner), [3] rho->z + transverse recursion.
  * qb_imad_peak measures the limb-product issue rate of this GPU (dependency-free IMAD.WIDE.U32 chains, 32 x 32 + 64 ->
  * 64, at full occupancy) in limb-MACs per second -- the denominator of the roofline for this path. */

@@ -1,7 +1,7 @@
 """Build the CUDA engine in-tree: qboot_b200/libqboot_b200.so (sm_100a only).
 
-Translation units: per limb count L one host-side engine (engine_inst.cu, -DQB_L) and five kernel groups
-(kernel_inst.cu, -DQB_L -DQB_KGROUP=0..4), plus the C ABI (capi.cu).  All device arithmetic is force-inlined into the
+Translation units: per limb count L one host-side engine (engine_inst.cu, -DQB_L) and seven kernel groups
+(kernel_inst.cu, -DQB_L -DQB_KGROUP=0..6), plus the C ABI (capi.cu).  All device arithmetic is force-inlined into the
 kernels (see mpf.cuh), so the kernel groups are the expensive part; they compile in parallel and are cached per object
 by a digest of its own preprocessed source.  No JIT cache, no torch extension machinery: the .so sits next to this file so that it
 travels with the repository snapshot to the GPU box.
