@@ -39,137 +39,92 @@ namespace qboot
 			uint64_t epoch = 0;  // arena generation the block belongs to
 		};
 	}
-	// sum_n y[n] M[n](x) >= M[N](x), sampled at x_0 .. x_D; M / chi is polynomial of degree <= D
+	// One matrix inequality  sum_n y[n] M[n](x) >= M[N](x)  for x >= 0, held as sample values at x_0 .. x_D; M / chi is a
+	// polynomial matrix of degree <= D.  After BootstrapEquation::convert the samples live in HBM (dev_) and the host copy
+	// stays empty until somebody asks for it.
 	class PolynomialInequality
 	{
+		using RealMatrix = algebra::Matrix<mp::real>;
+		using Samples = algebra::Vector<RealMatrix>;  // one matrix per sample point
 		uint32_t N_, sz_;
 		std::unique_ptr<ScaleFactor> chi_;
-		// host copy of the sample values mat_[n][k] (sz x sz); empty while the values only exist on the device
-		mutable algebra::Vector<algebra::Vector<algebra::Matrix<mp::real>>> mat_;
-		algebra::Vector<algebra::Matrix<mp::real>> target_{};
+		mutable algebra::Vector<Samples> mat_;  // mat_[n][k], sz x sz
+		Samples target_{};
 		b200::DeviceBlock dev_{};
 		// bilinear bases at the sample points when convert has already evaluated them (underneath its GPU phase)
-		std::optional<std::array<algebra::Matrix<mp::real>, 2>> bilinear_{};
-		friend class BootstrapEquation;
+		std::optional<std::array<RealMatrix, 2>> bilinear_{};
 		void fetch() const;  // device -> mat_
-		[[nodiscard]] algebra::Matrix<algebra::Polynomial> as_polynomial(algebra::Vector<algebra::Matrix<mp::real>>&& vals);
+		[[nodiscard]] mp::real scale_at(uint32_t k) const { return chi_->eval(chi_->sample_point(k)); }
+		[[nodiscard]] algebra::Matrix<algebra::Polynomial> as_polynomial(Samples&& vals);
+		friend class BootstrapEquation;
 		friend class PolynomialProgram;
 
 	public:
-		void _reset() &&
-		{
-			N_ = sz_ = 0;
-			chi_.reset();
-			std::move(mat_)._reset();
-			std::move(target_)._reset();
-			dev_ = {};
-		}
+		// scalar with a scale factor; scalar constant; matrix constant; matrix with a scale factor; device-resident samples
+		// with zero target
 		PolynomialInequality(uint32_t N, std::unique_ptr<ScaleFactor>&& scale, algebra::Vector<algebra::Vector<mp::real>>&& mat,
 		                     algebra::Vector<mp::real>&& target);
 		PolynomialInequality(uint32_t N, algebra::Vector<mp::real>&& mat, mp::real&& target);
-		PolynomialInequality(uint32_t N, uint32_t sz, algebra::Vector<algebra::Matrix<mp::real>>&& mat, algebra::Matrix<mp::real>&& target);
-		PolynomialInequality(uint32_t N, uint32_t sz, std::unique_ptr<ScaleFactor>&& scale,
-		                     algebra::Vector<algebra::Vector<algebra::Matrix<mp::real>>>&& mat,
-		                     algebra::Vector<algebra::Matrix<mp::real>>&& target);
-		// sample values resident on the device (zero target)
+		PolynomialInequality(uint32_t N, uint32_t sz, Samples&& mat, RealMatrix&& target);
+		PolynomialInequality(uint32_t N, uint32_t sz, std::unique_ptr<ScaleFactor>&& scale, algebra::Vector<Samples>&& mat, Samples&& target);
 		PolynomialInequality(uint32_t N, uint32_t sz, std::unique_ptr<ScaleFactor>&& scale, b200::DeviceBlock dev);
-		PolynomialInequality(const PolynomialInequality&) = delete;
-		PolynomialInequality& operator=(const PolynomialInequality&) = delete;
+		~PolynomialInequality() = default;
 		PolynomialInequality(PolynomialInequality&&) noexcept = default;
 		PolynomialInequality& operator=(PolynomialInequality&&) noexcept = default;
-		~PolynomialInequality() = default;
+		PolynomialInequality(const PolynomialInequality&) = delete;
+		PolynomialInequality& operator=(const PolynomialInequality&) = delete;
+		void _reset() &&;
 		[[nodiscard]] uint32_t num_of_variables() const { return N_; }
-		[[nodiscard]] uint32_t _total_memory() const { return (N_ + 1) * (max_degree() + 1) * sz_ * sz_; }
 		[[nodiscard]] uint32_t size() const { return sz_; }
 		[[nodiscard]] uint32_t max_degree() const { return chi_->max_degree(); }
+		[[nodiscard]] uint32_t _total_memory() const { return (N_ + 1) * (max_degree() + 1) * sz_ * sz_; }
 		[[nodiscard]] bool _on_device() const { return dev_.block >= 0; }
-		[[nodiscard]] algebra::Vector<algebra::Polynomial> bilinear_bases() const { return chi_->bilinear_bases(); }
 		[[nodiscard]] algebra::Vector<mp::real> sample_points() const { return chi_->sample_points(); }
 		[[nodiscard]] algebra::Vector<mp::real> sample_scalings() const { return chi_->sample_scalings(); }
+		[[nodiscard]] algebra::Vector<algebra::Polynomial> bilinear_bases() const { return chi_->bilinear_bases(); }
+		// Every accessor below CONSUMES what it returns, as in the reference.
+		// M[n](x_k) and M[N](x_k), with the factor chi(x_k) ...
+		[[nodiscard]] RealMatrix matrix_eval_with_scale(uint32_t n, uint32_t k) { return fetch(), std::move(mat_[n][k]); }
+		[[nodiscard]] RealMatrix target_eval_with_scale(uint32_t k) { return std::move(target_[k]); }
+		// ... and divided by it
+		[[nodiscard]] RealMatrix matrix_eval_without_scale(uint32_t n, uint32_t k) { return matrix_eval_with_scale(n, k) / scale_at(k); }
+		[[nodiscard]] RealMatrix target_eval_without_scale(uint32_t k) { return target_eval_with_scale(k) / scale_at(k); }
 		// M[n] / chi and M[N] / chi as polynomial matrices (interpolation through the sample points)
-		[[nodiscard]] algebra::Matrix<algebra::Polynomial> matrix_polynomial(uint32_t n)
-		{
-			fetch();
-			return as_polynomial(std::move(mat_[n]));
-		}
+		[[nodiscard]] algebra::Matrix<algebra::Polynomial> matrix_polynomial(uint32_t n) { return fetch(), as_polynomial(std::move(mat_[n])); }
 		[[nodiscard]] algebra::Matrix<algebra::Polynomial> target_polynomial() { return as_polynomial(std::move(target_)); }
-		// M[n](x_k), M[N](x_k): consumed by the call, as in the reference
-		[[nodiscard]] algebra::Matrix<mp::real> matrix_eval_with_scale(uint32_t n, uint32_t k)
-		{
-			fetch();
-			return std::move(mat_[n][k]);
-		}
-		[[nodiscard]] algebra::Matrix<mp::real> target_eval_with_scale(uint32_t k) { return std::move(target_[k]); }
-		[[nodiscard]] algebra::Matrix<mp::real> matrix_eval_without_scale(uint32_t n, uint32_t k)
-		{
-			fetch();
-			return std::move(mat_[n][k]) / chi_->eval(chi_->sample_point(k));
-		}
-		[[nodiscard]] algebra::Matrix<mp::real> target_eval_without_scale(uint32_t k)
-		{
-			return std::move(target_[k]) / chi_->eval(chi_->sample_point(k));
-		}
 	};
 
+	// maximize offset + objective . y  subject to equations (eliminated on the fly, one pivot each) and inequalities
 	class PolynomialProgram
 	{
 		uint32_t N_;
-		mp::real obj_const_{};
-		algebra::Vector<mp::real> obj_;
-		std::vector<algebra::Vector<mp::real>> equation_{};
-		std::vector<mp::real> equation_targets_{};
-		std::vector<uint32_t> leading_indices_{};  // pivots of the Gaussian elimination: y[leading_indices_[e]] is not free
-		std::vector<uint32_t> free_indices_{};
-		std::vector<std::optional<PolynomialInequality>> inequality_{};
-		std::shared_ptr<b200::Engine> engine_{};   // where create_input runs; taken from the first device-resident inequality
+		mp::real objective_offset_{};
+		algebra::Vector<mp::real> objective_;
+		std::vector<algebra::Vector<mp::real>> eq_rows_{};
+		std::vector<mp::real> eq_rhs_{};
+		std::vector<uint32_t> pivot_cols_{};  // y[pivot_cols_[e]] is fixed by equation e
+		std::vector<uint32_t> free_cols_{};   // the others, ascending
+		std::vector<std::optional<PolynomialInequality>> ineqs_{};
+		std::shared_ptr<b200::Engine> engine_{};  // where create_input runs; taken from the first device-resident inequality
 		// objective after elimination: (constant, coefficients of the free variables)
 		std::pair<mp::real, algebra::Vector<mp::real>> eliminated_objective();
 
 	public:
-		void _reset() &&
-		{
-			N_ = 0;
-			std::move(obj_const_)._reset();
-			std::move(obj_)._reset();
-			std::vector<algebra::Vector<mp::real>>{}.swap(equation_);
-			std::vector<mp::real>{}.swap(equation_targets_);
-			std::vector<uint32_t>{}.swap(leading_indices_);
-			std::vector<uint32_t>{}.swap(free_indices_);
-			std::vector<std::optional<PolynomialInequality>>{}.swap(inequality_);
-			engine_.reset();
-		}
-		explicit PolynomialProgram(uint32_t num_of_vars) : N_(num_of_vars), obj_(num_of_vars)
-		{
-			for (uint32_t i = 0; i < N_; ++i) free_indices_.push_back(i);
-		}
+		explicit PolynomialProgram(uint32_t num_of_vars);
+		void _reset() &&;
 		[[nodiscard]] uint32_t num_of_variables() const { return N_; }
-		[[nodiscard]] uint32_t num_of_inequalities() const { return uint32_t(inequality_.size()); }
-		[[nodiscard]] uint32_t _total_memory() const
-		{
-			uint32_t sum = 1 + obj_.size();
-			for (const auto& x : inequality_)
-				if (x) sum += x->_total_memory();
-			for (const auto& x : equation_) sum += x.size() + 1;
-			return sum;
-		}
-		[[nodiscard]] mp::real& objective_constant() { return obj_const_; }
-		[[nodiscard]] const mp::real& objective_constant() const { return obj_const_; }
-		[[nodiscard]] const algebra::Vector<mp::real>& objectives() const { return obj_; }
-		void objectives(algebra::Vector<mp::real>&& obj) &
-		{
-			assert(obj.size() == N_);
-			obj_ = std::move(obj);
-		}
+		[[nodiscard]] uint32_t num_of_inequalities() const { return uint32_t(ineqs_.size()); }
+		[[nodiscard]] uint32_t _total_memory() const;
+		[[nodiscard]] const mp::real& objective_constant() const { return objective_offset_; }
+		[[nodiscard]] mp::real& objective_constant() { return objective_offset_; }
+		[[nodiscard]] const algebra::Vector<mp::real>& objectives() const { return objective_; }
+		void objectives(algebra::Vector<mp::real>&& obj) &;
 		void _use_engine(std::shared_ptr<b200::Engine> e) & { engine_ = std::move(e); }
-		// y (all N variables) from z (the free ones) through the equations
-		algebra::Vector<mp::real> recover(const algebra::Vector<mp::real>& z);
 		// add sum_n y[n] vec[n] = target; equations must be independent; the order of calls fixes the output
 		void add_equation(algebra::Vector<mp::real>&& vec, mp::real&& target) &;
-		void add_inequality(std::optional<PolynomialInequality>&& ineq) &
-		{
-			assert(ineq->num_of_variables() == N_);
-			inequality_.push_back(std::move(ineq));
-		}
+		void add_inequality(std::optional<PolynomialInequality>&& ineq) &;
+		// y (all N variables) from z (the free ones) through the equations
+		algebra::Vector<mp::real> recover(const algebra::Vector<mp::real>& z);
 		SDPBInput create_input(uint32_t parallel = 1, const std::unique_ptr<_event_base>& event = {}) &&;
 		XMLInput create_xml(uint32_t parallel = 1, const std::unique_ptr<_event_base>& event = {}) &&;
 	};

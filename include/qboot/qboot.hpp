@@ -1,23 +1,29 @@
-// qboot_b200 façade -- umbrella header: `#include "qboot/qboot.hpp"` as with the reference (include/qboot/qboot.hpp).
+// qboot_b200 façade -- umbrella header: a program written for the reference says `#include "qboot/qboot.hpp"` and gets
+// the whole call surface.  Listed by layer, bottom up; paths are relative to this directory.
 #ifndef QBOOT_B200_QBOOT_HPP_
 #define QBOOT_B200_QBOOT_HPP_
-#include "qboot/algebra/complex_function.hpp"
-#include "qboot/algebra/matrix.hpp"
-#include "qboot/algebra/polynomial.hpp"
-#include "qboot/algebra/real_function.hpp"
-#include "qboot/block.hpp"
-#include "qboot/bootstrap_equation.hpp"
-#include "qboot/conformal_scale.hpp"
-#include "qboot/context.hpp"
-#include "qboot/hor_formula.hpp"
-#include "qboot/hor_recursion.hpp"
-#include "qboot/mp/rational.hpp"
-#include "qboot/mp/real.hpp"
-#include "qboot/my_filesystem.hpp"
-#include "qboot/polynomial_program.hpp"
-#include "qboot/primary_op.hpp"
-#include "qboot/scale_factor.hpp"
-#include "qboot/sdpb_input.hpp"
-#include "qboot/task_queue.hpp"
-#include "qboot/xml_input.hpp"
+// numbers (records of the engine behind MPFR-compatible classes) and the host pool
+#include "mp/real.hpp"
+#include "mp/rational.hpp"
+#include "task_queue.hpp"
+#include "my_filesystem.hpp"
+// containers and function spaces
+#include "algebra/matrix.hpp"
+#include "algebra/polynomial.hpp"
+#include "algebra/real_function.hpp"
+#include "algebra/complex_function.hpp"
+// the model description: operators, blocks, scale factors
+#include "primary_op.hpp"
+#include "block.hpp"
+#include "scale_factor.hpp"
+#include "conformal_scale.hpp"
+// the engine-backed Context and the table entry points
+#include "context.hpp"
+#include "hor_formula.hpp"
+#include "hor_recursion.hpp"
+// from crossing equations to SDPB input
+#include "bootstrap_equation.hpp"
+#include "polynomial_program.hpp"
+#include "sdpb_input.hpp"
+#include "xml_input.hpp"
 #endif  // QBOOT_B200_QBOOT_HPP_

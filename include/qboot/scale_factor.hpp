@@ -1,5 +1,6 @@
-// qboot_b200 façade -- the positive prefactor chi_j(x) of one polynomial inequality (call surface of
-// include/qboot/scale_factor.hpp): degree bound, sample points x_k, sample scalings chi(x_k), bilinear bases q_m(x).
+// qboot_b200 façade -- the positive prefactor chi_j(x) of one polynomial inequality (call surface of the reference's
+// include/qboot/scale_factor.hpp).  User code may derive its own; the planner only needs the six queries below and calls
+// them from host threads while the GPU works on the tables (qboot_b200/host/facade_program.cpp, Plan).
 #ifndef QBOOT_B200_SCALE_FACTOR_HPP_
 #define QBOOT_B200_SCALE_FACTOR_HPP_
 
@@ -11,41 +12,51 @@
 
 namespace qboot
 {
+	// Queries, with D = max_degree():
+	//   eval(v)            chi(v) for v >= 0
+	//   sample_point(k)    x_k,  k = 0..D          sample_points()    all of them
+	//   sample_scalings()  chi(x_0) .. chi(x_D)
+	//   bilinear_bases()   q_0 .. q_{D/2}, orthogonal under chi
 	class ScaleFactor
 	{
+	protected:
+		using Reals = algebra::Vector<mp::real>;
+		using Polys = algebra::Vector<algebra::Polynomial>;
+
 	public:
 		ScaleFactor() = default;
-		ScaleFactor(const ScaleFactor&) = default;
-		ScaleFactor& operator=(const ScaleFactor&) = default;
-		ScaleFactor(ScaleFactor&&) noexcept = default;
-		ScaleFactor& operator=(ScaleFactor&&) noexcept = default;
 		virtual ~ScaleFactor();
-		[[nodiscard]] virtual uint32_t max_degree() const = 0;                               // D
-		[[nodiscard]] virtual mp::real eval(const mp::real& v) const = 0;                    // chi(v), v >= 0
-		[[nodiscard]] virtual algebra::Vector<mp::real> sample_scalings() const = 0;         // chi(x_0..x_D)
-		[[nodiscard]] virtual mp::real sample_point(uint32_t k) const = 0;                   // x_k
-		[[nodiscard]] virtual algebra::Vector<mp::real> sample_points() const = 0;           // x_0..x_D
-		[[nodiscard]] virtual algebra::Vector<algebra::Polynomial> bilinear_bases() const = 0;  // q_0..q_{D/2}
+		ScaleFactor(const ScaleFactor&) = default;
+		ScaleFactor(ScaleFactor&&) noexcept = default;
+		ScaleFactor& operator=(const ScaleFactor&) = default;
+		ScaleFactor& operator=(ScaleFactor&&) noexcept = default;
+
+		[[nodiscard]] virtual uint32_t max_degree() const = 0;
+		[[nodiscard]] virtual mp::real eval(const mp::real& v) const = 0;
+		[[nodiscard]] virtual mp::real sample_point(uint32_t k) const = 0;
+		[[nodiscard]] virtual Reals sample_points() const = 0;
+		[[nodiscard]] virtual Reals sample_scalings() const = 0;
+		[[nodiscard]] virtual Polys bilinear_bases() const = 0;
 	};
-	// chi = 1, degree 0: constraints that do not depend on x (discrete sectors)
-	class TrivialScale : public ScaleFactor
+
+	// chi = 1 with D = 0: the factor of a constraint that does not depend on x (discrete sectors).  Move-only, like every
+	// scale factor the library hands out; bodies in qboot_b200/host/facade_math.cpp.
+	class TrivialScale final : public ScaleFactor
 	{
 	public:
 		TrivialScale() = default;
-		TrivialScale(const TrivialScale&) = delete;
-		TrivialScale& operator=(const TrivialScale&) = delete;
+		~TrivialScale() override;
 		TrivialScale(TrivialScale&&) noexcept = default;
 		TrivialScale& operator=(TrivialScale&&) noexcept = default;
-		~TrivialScale() override;
-		[[nodiscard]] uint32_t max_degree() const override { return 0; }
-		[[nodiscard]] mp::real eval([[maybe_unused]] const mp::real& v) const override { return mp::real(1); }
-		[[nodiscard]] algebra::Vector<mp::real> sample_scalings() const override { return algebra::Vector<mp::real>{mp::real(1)}; }
-		[[nodiscard]] mp::real sample_point([[maybe_unused]] uint32_t k) const override { return mp::real(0); }
-		[[nodiscard]] algebra::Vector<mp::real> sample_points() const override { return algebra::Vector<mp::real>{mp::real(1)}; }
-		[[nodiscard]] algebra::Vector<algebra::Polynomial> bilinear_bases() const override
-		{
-			return algebra::Vector<algebra::Polynomial>{algebra::Polynomial(mp::real(1))};
-		}
+		TrivialScale(const TrivialScale&) = delete;
+		TrivialScale& operator=(const TrivialScale&) = delete;
+
+		[[nodiscard]] uint32_t max_degree() const override;
+		[[nodiscard]] mp::real eval(const mp::real& v) const override;
+		[[nodiscard]] mp::real sample_point(uint32_t k) const override;
+		[[nodiscard]] Reals sample_points() const override;
+		[[nodiscard]] Reals sample_scalings() const override;
+		[[nodiscard]] Polys bilinear_bases() const override;
 	};
 }  // namespace qboot
 

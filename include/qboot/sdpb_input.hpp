@@ -28,86 +28,58 @@ namespace qboot
 		class Engine;
 		struct PackedProgram;  // the packed arrays of one create_input on the device
 	}
-	// Tr(A_p Y) + (B y)_p = c_p for p <-> (r, s <= r, k): one positivity constraint of the dual program
+	// One positivity constraint of the dual program: Tr(A_p Y) + (B y)_p = c_p with p <-> (r, s <= r, k).  B and c live
+	// either on the host (built by user code) or as entry `slot` of a packed program in HBM; the host copies appear on demand.
 	class DualConstraint
 	{
-		uint32_t dim_{}, deg_{};
-		mutable algebra::Matrix<mp::real> constraint_B_{};
-		mutable algebra::Vector<mp::real> constraint_c_{};
-		std::array<algebra::Matrix<mp::real>, 2> bilinear_{};
-		std::shared_ptr<b200::PackedProgram> dev_{};  // set when B and c live on the device
+		using RealMatrix = algebra::Matrix<mp::real>;
+		using Bases = std::array<RealMatrix, 2>;
+		struct Shape
+		{
+			uint32_t dim = 0, deg = 0;
+		};
+		Shape shape_{};
+		mutable RealMatrix host_B_{};
+		mutable algebra::Vector<mp::real> host_c_{};
+		Bases bilinear_{};
+		std::shared_ptr<b200::PackedProgram> dev_{};
 		int32_t slot_ = -1, cols_ = 0;
 		void fetch() const;
 		friend class SDPBInput;
 
 	public:
-		void _reset() &&
-		{
-			dim_ = deg_ = 0;
-			std::move(constraint_B_)._reset();
-			std::move(constraint_c_)._reset();
-			for (auto&& x : bilinear_) std::move(x)._reset();
-			dev_.reset();
-			slot_ = -1;
-		}
 		DualConstraint() = default;
-		DualConstraint(uint32_t dim, uint32_t deg, algebra::Matrix<mp::real>&& B, algebra::Vector<mp::real>&& c,
-		               std::array<algebra::Matrix<mp::real>, 2>&& bilinear);
-		// B and c stay on the device as entry `slot` of a packed program (cols = number of free variables)
-		DualConstraint(uint32_t dim, uint32_t deg, std::shared_ptr<b200::PackedProgram> dev, int32_t slot, int32_t cols,
-		               std::array<algebra::Matrix<mp::real>, 2>&& bilinear);
-		[[nodiscard]] uint32_t dim() const { return dim_; }
-		[[nodiscard]] uint32_t degree() const { return deg_; }
-		[[nodiscard]] uint32_t schur_size() const { return (deg_ + 1) * dim_ * (dim_ + 1) / 2; }
-		[[nodiscard]] const std::array<algebra::Matrix<mp::real>, 2>& bilinear() const { return bilinear_; }
-		[[nodiscard]] uint32_t _total_memory() const
-		{
-			uint32_t sum = schur_size() * (uint32_t(dev_ ? cols_ : int32_t(constraint_B_.column())) + 1);
-			for (const auto& q : bilinear_) sum += q.row() * q.column();
-			return sum;
-		}
-		[[nodiscard]] uint32_t num_free() const { return dev_ ? uint32_t(cols_) : constraint_B_.column(); }
-		// host copies (read back from the device on first use)
-		[[nodiscard]] const algebra::Matrix<mp::real>& obj_B() const
-		{
-			fetch();
-			return constraint_B_;
-		}
-		[[nodiscard]] const algebra::Vector<mp::real>& obj_c() const
-		{
-			fetch();
-			return constraint_c_;
-		}
+		DualConstraint(uint32_t dim, uint32_t deg, RealMatrix&& B, algebra::Vector<mp::real>&& c, Bases&& bilinear);
+		// device-resident B and c (cols = number of free variables)
+		DualConstraint(uint32_t dim, uint32_t deg, std::shared_ptr<b200::PackedProgram> dev, int32_t slot, int32_t cols, Bases&& bilinear);
+		void _reset() &&;
+		[[nodiscard]] uint32_t dim() const { return shape_.dim; }
+		[[nodiscard]] uint32_t degree() const { return shape_.deg; }
+		// rows of B: one per (sample point, upper-triangle entry)
+		[[nodiscard]] uint32_t schur_size() const { return (shape_.deg + 1) * shape_.dim * (shape_.dim + 1) / 2; }
+		[[nodiscard]] uint32_t num_free() const { return dev_ ? uint32_t(cols_) : host_B_.column(); }
+		[[nodiscard]] const Bases& bilinear() const { return bilinear_; }
+		[[nodiscard]] uint32_t _total_memory() const;  // numbers held, the reference's progress measure
+		[[nodiscard]] const RealMatrix& obj_B() const { return fetch(), host_B_; }
+		[[nodiscard]] const algebra::Vector<mp::real>& obj_c() const { return fetch(), host_c_; }
 	};
 
-	// maximize b_0 + sum_n b_n y_n subject to the constraints
+	// maximize offset + sum_n weights[n] y[n] subject to the constraints; slots are filled in any order
 	class SDPBInput
 	{
-		mp::real constant_term_;
-		algebra::Vector<mp::real> objectives_;
-		std::unique_ptr<std::optional<DualConstraint>[]> constraints_;
-		uint32_t num_constraints_;
+		mp::real offset_;
+		algebra::Vector<mp::real> weights_;
+		std::vector<std::optional<DualConstraint>> slots_;
 		void write_all(const fs::path& root, uint32_t parallel, const std::unique_ptr<_event_base>& event) const;
 
 	public:
-		void _reset() &&
-		{
-			std::move(constant_term_)._reset();
-			std::move(objectives_)._reset();
-			constraints_.reset();
-			num_constraints_ = 0;
-		}
 		SDPBInput(mp::real&& constant, algebra::Vector<mp::real>&& obj, uint32_t num_constraints);
-		[[nodiscard]] uint32_t num_constraints() const { return num_constraints_; }
-		[[nodiscard]] uint32_t _total_memory() const
-		{
-			uint32_t sum = 1 + objectives_.size();
-			for (uint32_t i = 0; i < num_constraints_; ++i)
-				if (constraints_[i].has_value()) sum += constraints_[i].value()._total_memory();
-			return sum;
-		}
+		void _reset() &&;
+		[[nodiscard]] uint32_t num_constraints() const { return uint32_t(slots_.size()); }
+		[[nodiscard]] uint32_t _total_memory() const;
 		void register_constraint(uint32_t index, DualConstraint&& c) &;
-		[[nodiscard]] const DualConstraint& constraint(uint32_t index) const { return constraints_[index].value(); }
+		[[nodiscard]] const DualConstraint& constraint(uint32_t index) const { return slots_[index].value(); }
+		// the directory SDPB reads; the rvalue form releases every constraint as soon as its files are written
 		void write(const fs::path& root, uint32_t parallel = 1, const std::unique_ptr<_event_base>& event = {}) const&;
 		void write(const fs::path& root, uint32_t parallel = 1, const std::unique_ptr<_event_base>& event = {}) &&;
 	};

@@ -1,13 +1,13 @@
-// qboot_b200 façade -- SDPB-1 style XML input (call surface of include/qboot/xml_input.hpp, src/xml_input.cpp:102-138).
-// Legacy output: explicit polynomial coefficients instead of sample values.  Host side only; the polynomials come from
-// interpolating the sample values of a program (PolynomialProgram::create_xml).
+// qboot_b200 façade -- SDPB-1 style XML input (call surface of the reference's include/qboot/xml_input.hpp; written by
+// src/xml_input.cpp:102-138 there).  Legacy output: explicit polynomial coefficients instead of sample values.  Host side
+// only; the polynomials come from interpolating the sample values of a program (PolynomialProgram::create_xml).
 #ifndef QBOOT_B200_XML_INPUT_HPP_
 #define QBOOT_B200_XML_INPUT_HPP_
 
 #include <cstdint>
-#include <memory>
 #include <optional>
 #include <utility>
+#include <vector>
 
 #include "qboot/algebra/matrix.hpp"
 #include "qboot/algebra/polynomial.hpp"
@@ -16,53 +16,53 @@
 
 namespace qboot
 {
-	// one polynomial vector matrix: M(r, c)[0] is the target, [1 + m] multiplies the m-th free variable
+	// One polynomial vector matrix.  Entry (r, c) is a vector of polynomials: [0] the target, [1 + m] the coefficient of the
+	// m-th free variable.  Size, degree and variable count are read off the containers; nothing is cached.
 	class PVM
 	{
-		uint32_t dim_{}, deg_{}, num_of_vars_{};
-		algebra::Matrix<algebra::Vector<algebra::Polynomial>> M_{};
-		algebra::Vector<mp::real> sample_points_{}, sample_scalings_{};
-		algebra::Vector<algebra::Polynomial> bilinear_{};
+		using PolyVectors = algebra::Matrix<algebra::Vector<algebra::Polynomial>>;
+		struct Payload
+		{
+			PolyVectors entries{};
+			algebra::Vector<mp::real> points{}, scalings{};
+			algebra::Vector<algebra::Polynomial> bases{};
+		};
+		Payload data_{};
 
 	public:
-		void _reset() &&
-		{
-			dim_ = deg_ = num_of_vars_ = 0;
-			std::move(M_)._reset();
-			std::move(sample_points_)._reset();
-			std::move(sample_scalings_)._reset();
-			std::move(bilinear_)._reset();
-		}
 		PVM() = default;
-		PVM(algebra::Matrix<algebra::Vector<algebra::Polynomial>>&& M, algebra::Vector<mp::real>&& x, algebra::Vector<mp::real>&& scale,
-		    algebra::Vector<algebra::Polynomial>&& bilinear)
-		    : dim_(M.row()), deg_(x.size() - 1), num_of_vars_(M.at(0, 0).size() - 1), M_(std::move(M)), sample_points_(std::move(x)),
-		      sample_scalings_(std::move(scale)), bilinear_(std::move(bilinear))
+		PVM(PolyVectors&& M, algebra::Vector<mp::real>&& x, algebra::Vector<mp::real>&& scale, algebra::Vector<algebra::Polynomial>&& bilinear)
 		{
+			data_.entries = std::move(M);
+			data_.points = std::move(x);
+			data_.scalings = std::move(scale);
+			data_.bases = std::move(bilinear);
 		}
-		[[nodiscard]] uint32_t dim() const { return dim_; }
-		[[nodiscard]] uint32_t deg() const { return deg_; }
-		[[nodiscard]] uint32_t num_of_vars() const { return num_of_vars_; }
-		[[nodiscard]] const algebra::Vector<mp::real>& sample_points() const { return sample_points_; }
-		[[nodiscard]] const algebra::Vector<mp::real>& sample_scalings() const { return sample_scalings_; }
-		[[nodiscard]] const algebra::Matrix<algebra::Vector<algebra::Polynomial>>& matrices() const { return M_; }
-		[[nodiscard]] const algebra::Vector<algebra::Polynomial>& bilinear() const { return bilinear_; }
+		// early release of the storage, the reference's idiom for consumed objects
+		void _reset() && { data_ = Payload{}; }
+		[[nodiscard]] uint32_t dim() const { return data_.entries.row(); }
+		[[nodiscard]] uint32_t deg() const { return data_.points.size() == 0 ? 0 : data_.points.size() - 1; }
+		[[nodiscard]] uint32_t num_of_vars() const { return dim() == 0 ? 0 : data_.entries.at(0, 0).size() - 1; }
+		[[nodiscard]] const PolyVectors& matrices() const { return data_.entries; }
+		[[nodiscard]] const algebra::Vector<mp::real>& sample_points() const { return data_.points; }
+		[[nodiscard]] const algebra::Vector<mp::real>& sample_scalings() const { return data_.scalings; }
+		[[nodiscard]] const algebra::Vector<algebra::Polynomial>& bilinear() const { return data_.bases; }
 	};
+	// The whole program: an objective vector ([0] the constant term, [1 + m] the free variables) and a slot per constraint,
+	// filled in any order (PolynomialProgram::create_xml fills them from its host threads).
 	class XMLInput
 	{
-		algebra::Vector<mp::real> objectives_;  // [0] the constant, [1 + m] the free variables
-		std::unique_ptr<std::optional<PVM>[]> constraints_;
-		uint32_t num_constraints_;
+		algebra::Vector<mp::real> objective_row_;
+		std::vector<std::optional<PVM>> slots_;
 
 	public:
+		XMLInput(mp::real&& constant, algebra::Vector<mp::real>&& obj, uint32_t num_constraints);
 		void _reset() &&
 		{
-			std::move(objectives_)._reset();
-			constraints_.reset();
-			num_constraints_ = 0;
+			std::move(objective_row_)._reset();
+			slots_.clear();
 		}
-		XMLInput(mp::real&& constant, algebra::Vector<mp::real>&& obj, uint32_t num_constraints);
-		[[nodiscard]] uint32_t num_constraints() const { return num_constraints_; }
+		[[nodiscard]] uint32_t num_constraints() const { return uint32_t(slots_.size()); }
 		void register_constraint(uint32_t index, PVM&& c) &;
 		void write(const fs::path& path) const;
 	};

@@ -320,13 +320,13 @@ namespace qboot
 	std::string PrimaryOperator::str() const
 	{
 		std::ostringstream os;
-		os << "operator(spin=" << spin_ << ", dim=" << 2 * epsilon_ + 2 << ", delta=" << delta_ << ")";
+		os << "operator(spin=" << spin() << ", dim=" << 2 * eps_ + 2 << ", delta=" << delta() << ")";
 		return os.str();
 	}
 	std::string GeneralPrimaryOperator::str() const
 	{
 		std::ostringstream os;
-		os << "operator(spin=" << spin_ << ", dim=" << 2 * epsilon_ + 2 << ", delta in [" << from_ << ", " << (to_.has_value() ? to_.value().str() : "infty")
+		os << "operator(spin=" << spin_ << ", dim=" << 2 * eps_ + 2 << ", delta in [" << lower_bound() << ", " << (is_finite() ? upper_bound().str() : "infty")
 		   << "))";
 		return os.str();
 	}

@@ -178,6 +178,13 @@ namespace qboot
 
 	ScaleFactor::~ScaleFactor() = default;
 	TrivialScale::~TrivialScale() = default;
+	// the constant factor: one sample (the reference puts it at x = 1 in the list and at 0 in the single query), value 1
+	uint32_t TrivialScale::max_degree() const { return 0; }
+	mp::real TrivialScale::eval(const mp::real&) const { return mp::real(1); }
+	mp::real TrivialScale::sample_point(uint32_t) const { return mp::real(0); }
+	ScaleFactor::Reals TrivialScale::sample_points() const { return Reals{mp::real(1)}; }
+	ScaleFactor::Reals TrivialScale::sample_scalings() const { return Reals{mp::real(1)}; }
+	ScaleFactor::Polys TrivialScale::bilinear_bases() const { return Polys{algebra::Polynomial(mp::real(1))}; }
 	ConformalScale::~ConformalScale() = default;
 
 	namespace

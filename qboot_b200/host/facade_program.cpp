@@ -16,6 +16,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <numeric>
 #include <sstream>
 #include <thread>
 #include <unordered_map>
@@ -514,6 +515,15 @@ namespace qboot
 		target_ = Vector<Matrix<real>>(deg + 1);
 		for (uint32_t k = 0; k <= deg; ++k) target_[k] = Matrix<real>(sz, sz);
 	}
+	void PolynomialInequality::_reset() &&
+	{
+		N_ = sz_ = 0;
+		chi_.reset();
+		move(mat_)._reset();
+		move(target_)._reset();
+		bilinear_.reset();
+		dev_ = {};
+	}
 	void PolynomialInequality::fetch() const
 	{
 		if (mat_.size() == N_ || dev_.block < 0) return;
@@ -561,28 +571,63 @@ namespace qboot
 	// src/polynomial_program.cpp:103-116
 	Vector<real> PolynomialProgram::recover(const Vector<real>& z)
 	{
-		const uint32_t eq_sz = uint32_t(equation_.size()), M = N_ - eq_sz;
+		const uint32_t eq_sz = uint32_t(eq_rows_.size()), M = N_ - eq_sz;
 		assert(z.size() == M);
 		Vector<real> y(N_);
-		for (uint32_t n = 0; n < M; ++n) y[free_indices_[n]] = z[n];
+		for (uint32_t n = 0; n < M; ++n) y[free_cols_[n]] = z[n];
 		for (uint32_t e = 0; e < eq_sz; ++e)
 		{
-			const auto n = leading_indices_[e];
-			y[n] = equation_targets_[e];
-			for (uint32_t m = 0; m < M; ++m) y[n] -= equation_[e][free_indices_[m]] * z[m];
+			const auto n = pivot_cols_[e];
+			y[n] = eq_rhs_[e];
+			for (uint32_t m = 0; m < M; ++m) y[n] -= eq_rows_[e][free_cols_[m]] * z[m];
 		}
 		return y;
 	}
 	// Gaussian elimination step with the largest entry as pivot (src/polynomial_program.cpp:118-151)
+	PolynomialProgram::PolynomialProgram(uint32_t num_of_vars) : N_(num_of_vars), objective_(num_of_vars), free_cols_(num_of_vars)
+	{
+		std::iota(free_cols_.begin(), free_cols_.end(), 0u);
+	}
+	void PolynomialProgram::_reset() &&
+	{
+		N_ = 0;
+		move(objective_offset_)._reset();
+		move(objective_)._reset();
+		const auto release = [](auto& v) { std::decay_t<decltype(v)>().swap(v); };  // clear() would keep the capacity
+		release(eq_rows_);
+		release(eq_rhs_);
+		release(pivot_cols_);
+		release(free_cols_);
+		release(ineqs_);
+		engine_.reset();
+	}
+	uint32_t PolynomialProgram::_total_memory() const
+	{
+		uint32_t held = 1 + objective_.size();
+		for (const auto& q : ineqs_)
+			if (q.has_value()) held += q->_total_memory();
+		for (const auto& row : eq_rows_) held += row.size() + 1;
+		return held;
+	}
+	void PolynomialProgram::objectives(Vector<real>&& obj) &
+	{
+		assert(obj.size() == N_);
+		objective_ = move(obj);
+	}
+	void PolynomialProgram::add_inequality(std::optional<PolynomialInequality>&& ineq) &
+	{
+		assert(ineq.has_value() && ineq->num_of_variables() == N_);
+		ineqs_.push_back(move(ineq));
+	}
 	void PolynomialProgram::add_equation(Vector<real>&& vec, real&& target) &
 	{
 		assert(vec.size() == N_);
 		// reduce the new equation by the earlier ones
-		for (uint32_t e = 0; e < equation_.size(); ++e)
+		for (uint32_t e = 0; e < eq_rows_.size(); ++e)
 		{
-			const real t = vec[leading_indices_[e]];
-			target -= t * equation_targets_[e];
-			vec -= mul_scalar(t, equation_[e]);
+			const real t = vec[pivot_cols_[e]];
+			target -= t * eq_rhs_[e];
+			vec -= mul_scalar(t, eq_rows_[e]);
 		}
 		uint32_t pivot = 0;
 		for (uint32_t n = 1; n < N_; ++n)
@@ -592,29 +637,29 @@ namespace qboot
 		vec /= top;
 		vec[pivot] = 1;
 		// and the earlier ones by the new equation
-		for (uint32_t e = 0; e < equation_.size(); ++e)
+		for (uint32_t e = 0; e < eq_rows_.size(); ++e)
 		{
-			const real t = equation_[e][pivot];
-			equation_targets_[e] -= t * target;
-			equation_[e] -= mul_scalar(t, vec);
+			const real t = eq_rows_[e][pivot];
+			eq_rhs_[e] -= t * target;
+			eq_rows_[e] -= mul_scalar(t, vec);
 		}
-		equation_.push_back(move(vec));
-		equation_targets_.push_back(move(target));
-		leading_indices_.push_back(pivot);
-		free_indices_.erase(std::find(free_indices_.begin(), free_indices_.end(), pivot));
+		eq_rows_.push_back(move(vec));
+		eq_rhs_.push_back(move(target));
+		pivot_cols_.push_back(pivot);
+		free_cols_.erase(std::find(free_cols_.begin(), free_cols_.end(), pivot));
 	}
 	// objective in terms of the free variables (src/polynomial_program.cpp:162-170)
 	std::pair<real, Vector<real>> PolynomialProgram::eliminated_objective()
 	{
-		const uint32_t eq_sz = uint32_t(equation_.size()), M = N_ - eq_sz;
+		const uint32_t eq_sz = uint32_t(eq_rows_.size()), M = N_ - eq_sz;
 		Vector<real> obj_new(M);
-		for (uint32_t m = 0; m < M; ++m) obj_new[m] = obj_[free_indices_[m]];
-		real constant = obj_const_;
+		for (uint32_t m = 0; m < M; ++m) obj_new[m] = objective_[free_cols_[m]];
+		real constant = objective_offset_;
 		for (uint32_t e = 0; e < eq_sz; ++e)
 		{
-			const real t = obj_[leading_indices_[e]];
-			for (uint32_t m = 0; m < M; ++m) obj_new[m] -= equation_[e][free_indices_[m]] * t;
-			constant += equation_targets_[e] * t;
+			const real t = objective_[pivot_cols_[e]];
+			for (uint32_t m = 0; m < M; ++m) obj_new[m] -= eq_rows_[e][free_cols_[m]] * t;
+			constant += eq_rhs_[e] * t;
 		}
 		return {move(constant), move(obj_new)};
 	}
@@ -694,12 +739,12 @@ namespace qboot
 	// src/polynomial_program.cpp:152-232 -- the per-inequality loops run as ONE pack kernel over all blocks
 	SDPBInput PolynomialProgram::create_input(uint32_t parallel, const unique_ptr<_event_base>& event) &&
 	{
-		const uint32_t eq_sz = uint32_t(equation_.size()), M = N_ - eq_sz, J = uint32_t(inequality_.size());
+		const uint32_t eq_sz = uint32_t(eq_rows_.size()), M = N_ - eq_sz, J = uint32_t(ineqs_.size());
 		auto [constant, obj_new] = eliminated_objective();
 		SDPBInput sdpb(move(constant), move(obj_new), J);
 		// the engine that holds the device-resident blocks (or a fresh one for a program built from host data only)
 		std::shared_ptr<b200::Engine> eng = engine_;
-		for (const auto& q : inequality_)
+		for (const auto& q : ineqs_)
 			if (!eng && q->_on_device()) eng = q->dev_.engine;
 		if (!eng) eng = std::make_shared<b200::Engine>(mp::_prec(), 1u, 1u, mp::rational(1, 2));
 		const size_t W = size_t(eng->words);
@@ -715,7 +760,7 @@ namespace qboot
 			if (info[1] != int64_t(N_))
 			{
 				// nothing of this program is on the device yet: open an empty arena with N variables
-				for (const auto& q : inequality_)
+				for (const auto& q : ineqs_)
 					if (q->_on_device()) throw std::logic_error("qboot_b200: device blocks do not belong to this engine's current program");
 				const int32_t dim = int32_t(N_), sym = 1;
 				eng->check(qb_pmp_assemble(eng->h, 1, &dim, &sym, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr), "qb_pmp_assemble");
@@ -724,7 +769,7 @@ namespace qboot
 			vector<int32_t> sel(J);
 			for (uint32_t j = 0; j < J; ++j)
 			{
-				auto& q = inequality_[j].value();
+				auto& q = ineqs_[j].value();
 				if (q._on_device())
 				{
 					if (q.dev_.engine != eng || q.dev_.epoch != eng->epoch)
@@ -745,12 +790,12 @@ namespace qboot
 						}
 				sel[j] = eng->check(qb_pmp_block_add(eng->h, int(ns), int(sz), mat.data(), tgt.data()), "qb_pmp_block_add", true);
 			}
-			vector<int32_t> lead(leading_indices_.begin(), leading_indices_.end()), free_idx(free_indices_.begin(), free_indices_.end());
+			vector<int32_t> lead(pivot_cols_.begin(), pivot_cols_.end()), free_idx(free_cols_.begin(), free_cols_.end());
 			vector<uint32_t> eqn(W * size_t(eq_sz) * N_), eqt(W * size_t(eq_sz));
 			for (uint32_t e = 0; e < eq_sz; ++e)
 			{
-				for (uint32_t n = 0; n < N_; ++n) std::memcpy(eqn.data() + W * (size_t(e) * N_ + n), equation_[e][n]._words(), 4 * W);
-				std::memcpy(eqt.data() + W * e, equation_targets_[e]._words(), 4 * W);
+				for (uint32_t n = 0; n < N_; ++n) std::memcpy(eqn.data() + W * (size_t(e) * N_ + n), eq_rows_[e][n]._words(), 4 * W);
+				std::memcpy(eqt.data() + W * e, eq_rhs_[e]._words(), 4 * W);
 			}
 			eng->check(qb_pmp_pack(eng->h, int(J), sel.data(), int(eq_sz), lead.data(), int(M), free_idx.data(), eqn.data(), eqt.data()), "qb_pmp_pack");
 			packed->pack_epoch = ++eng->pack_epoch;
@@ -761,9 +806,9 @@ namespace qboot
 			vector<const ScaleFactor*> chis;
 			vector<uint32_t> which;
 			for (uint32_t j = 0; j < J; ++j)
-				if (!inequality_[j]->bilinear_)
+				if (!ineqs_[j]->bilinear_)
 				{
-					chis.push_back(inequality_[j]->chi_.get());
+					chis.push_back(ineqs_[j]->chi_.get());
 					which.push_back(j);
 				}
 			vector<BilinearSamples> prepared(chis.size());
@@ -777,49 +822,49 @@ namespace qboot
 			vector<const BilinearSamples*> smp;
 			for (const auto& x : prepared) smp.push_back(&x);
 			auto bl = bilinear_at_samples_batch(*eng, chis, smp);
-			for (size_t i = 0; i < which.size(); ++i) inequality_[which[i]]->bilinear_ = move(bl[i]);
+			for (size_t i = 0; i < which.size(); ++i) ineqs_[which[i]]->bilinear_ = move(bl[i]);
 		}
 		vector<std::function<int()>> tasks;
 		for (uint32_t j = 0; j < J; ++j)
 			tasks.emplace_back([this, &sdpb, &packed, j, M, &event] {
 				_scoped_event scope(std::to_string(j), event);
-				auto& ineq = inequality_[j].value();
+				auto& ineq = ineqs_[j].value();
 				const uint32_t sz = ineq.size(), deg = ineq.max_degree();
 				sdpb.register_constraint(j, DualConstraint(sz, deg, packed, int32_t(j), int32_t(M), move(*ineq.bilinear_)));
-				inequality_[j].reset();
+				ineqs_[j].reset();
 				return 0;
 			});
 		_parallel_evaluate(tasks, parallel);
-		equation_.clear();
-		equation_targets_.clear();
-		free_indices_.clear();
-		inequality_.clear();
-		leading_indices_.clear();
+		eq_rows_.clear();
+		eq_rhs_.clear();
+		free_cols_.clear();
+		ineqs_.clear();
+		pivot_cols_.clear();
 		return sdpb;
 	}
 	// src/polynomial_program.cpp:233-281 (host; legacy output)
 	XMLInput PolynomialProgram::create_xml(uint32_t parallel, const unique_ptr<_event_base>& event) &&
 	{
-		const uint32_t eq_sz = uint32_t(equation_.size()), M = N_ - eq_sz, J = uint32_t(inequality_.size());
+		const uint32_t eq_sz = uint32_t(eq_rows_.size()), M = N_ - eq_sz, J = uint32_t(ineqs_.size());
 		auto [constant, obj_new] = eliminated_objective();
 		XMLInput xml(move(constant), move(obj_new), J);
 		vector<std::function<int()>> tasks;
 		for (uint32_t j = 0; j < J; ++j)
 			tasks.emplace_back([this, &xml, j, M, eq_sz, &event] {
 				_scoped_event scope(std::to_string(j), event);
-				auto& ineq = inequality_[j].value();
+				auto& ineq = ineqs_[j].value();
 				const uint32_t sz = ineq.size();
 				Matrix<Vector<Polynomial>> mat(sz, sz);
 				for (uint32_t r = 0; r < sz; ++r)
 					for (uint32_t c = 0; c < sz; ++c) mat.at(r, c) = Vector<Polynomial>(M + 1);
 				Matrix<Polynomial> target = -ineq.target_polynomial();
 				Vector<Matrix<Polynomial>> new_mat(M);
-				for (uint32_t m = 0; m < M; ++m) new_mat[m] = ineq.matrix_polynomial(free_indices_[m]);
+				for (uint32_t m = 0; m < M; ++m) new_mat[m] = ineq.matrix_polynomial(free_cols_[m]);
 				for (uint32_t e = 0; e < eq_sz; ++e)
 				{
-					auto t = ineq.matrix_polynomial(leading_indices_[e]);
-					for (uint32_t m = 0; m < M; ++m) new_mat[m] -= mul_scalar(equation_[e][free_indices_[m]], t);
-					target += mul_scalar(equation_targets_[e], t);
+					auto t = ineq.matrix_polynomial(pivot_cols_[e]);
+					for (uint32_t m = 0; m < M; ++m) new_mat[m] -= mul_scalar(eq_rows_[e][free_cols_[m]], t);
+					target += mul_scalar(eq_rhs_[e], t);
 				}
 				for (uint32_t r = 0; r < sz; ++r)
 					for (uint32_t c = 0; c < sz; ++c)
@@ -828,15 +873,15 @@ namespace qboot
 						for (uint32_t m = 0; m < M; ++m) mat.at(r, c).at(m + 1) = move(new_mat[m].at(r, c));
 					}
 				xml.register_constraint(j, PVM(move(mat), ineq.sample_points(), ineq.sample_scalings(), ineq.bilinear_bases()));
-				inequality_[j].reset();
+				ineqs_[j].reset();
 				return 0;
 			});
 		_parallel_evaluate(tasks, parallel);
-		equation_.clear();
-		equation_targets_.clear();
-		free_indices_.clear();
-		inequality_.clear();
-		leading_indices_.clear();
+		eq_rows_.clear();
+		eq_rhs_.clear();
+		free_cols_.clear();
+		ineqs_.clear();
+		pivot_cols_.clear();
 		return xml;
 	}
 
@@ -887,18 +932,28 @@ namespace qboot
 	}  // namespace b200
 
 	DualConstraint::DualConstraint(uint32_t dim, uint32_t deg, Matrix<real>&& B, Vector<real>&& c, std::array<Matrix<real>, 2>&& bilinear)
-	    : dim_(dim), deg_(deg), constraint_B_(move(B)), constraint_c_(move(c)), bilinear_(move(bilinear))
+	    : shape_{dim, deg}, host_B_(move(B)), host_c_(move(c)), bilinear_(move(bilinear))
 	{
-		assert(constraint_B_.row() == schur_size() && constraint_c_.size() == schur_size());
+		assert(host_B_.row() == schur_size() && host_c_.size() == schur_size());
 	}
 	DualConstraint::DualConstraint(uint32_t dim, uint32_t deg, std::shared_ptr<b200::PackedProgram> dev, int32_t slot, int32_t cols,
 	                               std::array<Matrix<real>, 2>&& bilinear)
-	    : dim_(dim), deg_(deg), bilinear_(move(bilinear)), dev_(move(dev)), slot_(slot), cols_(cols)
+	    : shape_{dim, deg}, bilinear_(move(bilinear)), dev_(move(dev)), slot_(slot), cols_(cols)
 	{
+	}
+	void DualConstraint::_reset() &&
+	{
+		*this = DualConstraint{};
+	}
+	uint32_t DualConstraint::_total_memory() const
+	{
+		uint32_t held = schur_size() * (num_free() + 1);
+		for (const auto& q : bilinear_) held += q.row() * q.column();
+		return held;
 	}
 	void DualConstraint::fetch() const
 	{
-		if (!dev_ || constraint_c_.size() == schur_size()) return;
+		if (!dev_ || host_c_.size() == schur_size()) return;
 		auto& e = *dev_->engine;
 		const size_t W = size_t(e.words), schur = schur_size(), M = size_t(cols_);
 		vector<uint32_t> B(W * schur * M), c(W * schur);
@@ -907,24 +962,36 @@ namespace qboot
 			dev_->require_current();
 			e.check(qb_pmp_packed_fetch(e.h, slot_, B.data(), c.data()), "qb_pmp_packed_fetch");
 		}
-		constraint_B_ = Matrix<real>(uint32_t(schur), uint32_t(M));
-		constraint_c_ = Vector<real>(uint32_t(schur));
+		host_B_ = Matrix<real>(uint32_t(schur), uint32_t(M));
+		host_c_ = Vector<real>(uint32_t(schur));
 		for (size_t p = 0; p < schur; ++p)
 		{
-			for (size_t m = 0; m < M; ++m) constraint_B_.at(uint32_t(p), uint32_t(m)) = load_record(B.data() + W * (p * M + m), W);
-			constraint_c_[uint32_t(p)] = load_record(c.data() + W * p, W);
+			for (size_t m = 0; m < M; ++m) host_B_.at(uint32_t(p), uint32_t(m)) = load_record(B.data() + W * (p * M + m), W);
+			host_c_[uint32_t(p)] = load_record(c.data() + W * p, W);
 		}
 	}
 	SDPBInput::SDPBInput(real&& constant, Vector<real>&& obj, uint32_t num_constraints)
-	    : constant_term_(move(constant)), objectives_(move(obj)), constraints_(std::make_unique<std::optional<DualConstraint>[]>(num_constraints)),
-	      num_constraints_(num_constraints)
+	    : offset_(move(constant)), weights_(move(obj)), slots_(num_constraints)
 	{
+	}
+	void SDPBInput::_reset() &&
+	{
+		move(offset_)._reset();
+		move(weights_)._reset();
+		slots_.clear();
+	}
+	uint32_t SDPBInput::_total_memory() const
+	{
+		uint32_t held = 1 + weights_.size();
+		for (const auto& c : slots_)
+			if (c.has_value()) held += c->_total_memory();
+		return held;
 	}
 	void SDPBInput::register_constraint(uint32_t index, DualConstraint&& c) &
 	{
-		assert(index < num_constraints_ && !constraints_[index].has_value());
-		assert(objectives_.size() == c.num_free());
-		constraints_[index] = move(c);
+		assert(index < slots_.size() && !slots_[index].has_value());
+		assert(weights_.size() == c.num_free());
+		slots_[index] = move(c);
 	}
 	namespace
 	{
@@ -948,11 +1015,11 @@ namespace qboot
 		const auto root = root_ / "";
 		fs::create_directory(root);
 		const int nd = sdpb_digits();
-		const uint32_t J = num_constraints_;
+		const uint32_t J = num_constraints();
 		// the packed program shared by the device-resident constraints
 		std::shared_ptr<b200::PackedProgram> packed;
 		for (uint32_t j = 0; j < J; ++j)
-			if (constraints_[j]->dev_) packed = constraints_[j]->dev_;
+			if (slots_[j]->dev_) packed = slots_[j]->dev_;
 		// the device formats the large arrays while host threads write the small files (blocks, objectives, bilinear bases)
 		std::exception_ptr text_error;
 		std::thread text_thread;
@@ -985,17 +1052,17 @@ namespace qboot
 			out << 1 << "\n" << J << "\n";
 			for (uint32_t i = 0; i < J; ++i) out << i << "\n";
 			out << J << "\n";
-			for (uint32_t i = 0; i < J; ++i) out << constraints_[i]->dim() << "\n";
+			for (uint32_t i = 0; i < J; ++i) out << slots_[i]->dim() << "\n";
 			out << J << "\n";
-			for (uint32_t i = 0; i < J; ++i) out << constraints_[i]->degree() << "\n";
+			for (uint32_t i = 0; i < J; ++i) out << slots_[i]->degree() << "\n";
 			out << J << "\n";
-			for (uint32_t i = 0; i < J; ++i) out << constraints_[i]->schur_size() << "\n";
+			for (uint32_t i = 0; i < J; ++i) out << slots_[i]->schur_size() << "\n";
 			out << 2 * J << "\n";
 			for (uint32_t i = 0; i < J; ++i)
-				for (const auto& m : constraints_[i]->bilinear()) out << m.row() * constraints_[i]->dim() << "\n";
+				for (const auto& m : slots_[i]->bilinear()) out << m.row() * slots_[i]->dim() << "\n";
 			out << 2 * J << "\n";
 			for (uint32_t i = 0; i < J; ++i)
-				for (const auto& m : constraints_[i]->bilinear()) out << m.column() * constraints_[i]->dim() << "\n";
+				for (const auto& m : slots_[i]->bilinear()) out << m.column() * slots_[i]->dim() << "\n";
 			write_file(root / "blocks.0", out.str(), nullptr, 0);
 			return 0;
 		});
@@ -1005,14 +1072,14 @@ namespace qboot
 		for (uint32_t i = 0; i < J; ++i)
 			tasks.emplace_back([&, i] {
 				vector<uint32_t> recs;
-				for (const auto& m : constraints_[i]->bilinear()) append_records(recs, m, W);
+				for (const auto& m : slots_[i]->bilinear()) append_records(recs, m, W);
 				std::string text;
 				vector<size_t> ends;
 				b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, text, &ends);
 				std::string& out = bl_pieces[i];
 				out.reserve(text.size() + 64);
 				size_t pos = 0, num = 0;
-				for (const auto& m : constraints_[i]->bilinear())
+				for (const auto& m : slots_[i]->bilinear())
 				{
 					out += std::to_string(m.row()) + " " + std::to_string(m.column()) + "\n";
 					num += size_t(m.row()) * m.column();
@@ -1024,12 +1091,12 @@ namespace qboot
 			});
 		tasks.emplace_back([&] {
 			_scoped_event scope("write_objectives", event);
-			vector<uint32_t> recs(constant_term_._words(), constant_term_._words() + W);
-			for (const auto& x : objectives_) recs.insert(recs.end(), x._words(), x._words() + W);
+			vector<uint32_t> recs(offset_._words(), offset_._words() + W);
+			for (const auto& x : weights_) recs.insert(recs.end(), x._words(), x._words() + W);
 			std::string text;
 			b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, text);
 			const size_t first = text.find('\n') + 1;
-			std::string out = text.substr(0, first) + std::to_string(objectives_.size()) + "\n";
+			std::string out = text.substr(0, first) + std::to_string(weights_.size()) + "\n";
 			out.append(text, first, std::string::npos);
 			write_file(root / "objectives", out, nullptr, 0);
 			return 0;
@@ -1050,7 +1117,7 @@ namespace qboot
 		for (uint32_t i = 0; i < J; ++i)
 			tasks.emplace_back([&, i] {
 				_scoped_event scope("write constraint " + std::to_string(i), event);
-				const auto& c = constraints_[i].value();
+				const auto& c = slots_[i].value();
 				const std::string hb = std::to_string(c.schur_size()) + " " + std::to_string(c.num_free()) + "\n", hc = std::to_string(c.schur_size()) + "\n";
 				if (c.dev_)
 				{
@@ -1062,11 +1129,11 @@ namespace qboot
 				else
 				{
 					vector<uint32_t> recs;
-					append_records(recs, c.constraint_B_, W);
+					append_records(recs, c.host_B_, W);
 					std::string tb, tc;
 					b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, tb);
 					recs.clear();
-					for (const auto& x : c.constraint_c_) recs.insert(recs.end(), x._words(), x._words() + W);
+					for (const auto& x : c.host_c_) recs.insert(recs.end(), x._words(), x._words() + W);
 					b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, tc);
 					write_file(root / ("free_var_matrix." + std::to_string(i)), hb, tb.data(), tb.size());
 					write_file(root / ("primal_objective_c." + std::to_string(i)), hc, tc.data(), tc.size());
@@ -1079,21 +1146,20 @@ namespace qboot
 	void SDPBInput::write(const fs::path& root, uint32_t parallel, const unique_ptr<_event_base>& event) &&
 	{
 		write_all(root, parallel, event);
-		move(objectives_)._reset();
-		for (uint32_t i = 0; i < num_constraints_; ++i) constraints_[i].reset();
+		move(weights_)._reset();
+		for (auto& c : slots_) c.reset();
 	}
 
 	// ---- XML (src/xml_input.cpp:80-138) --------------------------------------------------------------------------------------
-	XMLInput::XMLInput(real&& constant, Vector<real>&& obj, uint32_t num_constraints)
-	    : objectives_(obj.size() + 1), constraints_(std::make_unique<std::optional<PVM>[]>(num_constraints)), num_constraints_(num_constraints)
+	XMLInput::XMLInput(real&& constant, Vector<real>&& obj, uint32_t num_constraints) : objective_row_(obj.size() + 1), slots_(num_constraints)
 	{
-		objectives_[0] = move(constant);
-		for (uint32_t i = 0; i < obj.size(); ++i) objectives_[i + 1] = obj[i];
+		objective_row_[0] = move(constant);
+		for (uint32_t i = 0; i < obj.size(); ++i) objective_row_[i + 1] = obj[i];
 	}
 	void XMLInput::register_constraint(uint32_t index, PVM&& c) &
 	{
-		assert(index < num_constraints_ && !constraints_[index].has_value());
-		constraints_[index] = move(c);
+		assert(index < slots_.size() && !slots_[index].has_value());
+		slots_[index] = move(c);
 	}
 	void XMLInput::write(const fs::path& path) const
 	{
@@ -1130,11 +1196,11 @@ namespace qboot
 			close("polynomial");
 		};
 		open("sdp");
-		vec(objectives_, "objective");
+		vec(objective_row_, "objective");
 		open("polynomialVectorMatrices");
-		for (uint32_t j = 0; j < num_constraints_; ++j)
+		for (size_t j = 0; j < slots_.size(); ++j)
 		{
-			const auto& c = constraints_[j].value();
+			const auto& c = slots_[j].value();
 			open("polynomialVectorMatrix");
 			open("rows");
 			f << c.dim();
