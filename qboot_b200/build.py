@@ -30,7 +30,7 @@ CXX = os.environ.get("QB_CXX", "/usr/bin/g++")
 
 # limb counts compiled in: 512, 600, 800, 1000/1024, 1200, 1536 bits (override: QB_LIMBS=19,32)
 LIMBS = tuple(int(x) for x in os.environ.get("QB_LIMBS", "16,19,25,32,38,48").split(","))
-KGROUPS = (0, 1, 2, 3, 4, 5, 6)
+KGROUPS = (0, 1, 2, 3, 4, 5, 6, 7)
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -1,12 +1,13 @@
-// qboot_b200 -- kernel translation unit: nvcc -DQB_L=<limbs> -DQB_KGROUP=<0..6> kernel_inst.cu
+// qboot_b200 -- kernel translation unit: nvcc -DQB_L=<limbs> -DQB_KGROUP=<0..7> kernel_inst.cu
 //   group 0: k_rec_coeffs, k_ops    1: k_series    2: k_scale, k_horner    3: k_rho_to_z, k_offdiag_val, k_offdiag_close    4: k_vtod, k_fblock, k_pow
 //   group 6: k_horner (its own unit so that k_scale and k_horner can differ in QB_COLD_COPY)
+//   group 7: k_series_coop (small batches: eight warps per 32 jobs)
 //   group 5: k_pmp_accum, k_pmp_pack, k_dec_format, k_dec_gather (the last one is not templated: compiled once, -DQB_L_FIRST=<smallest L>)
 #if !defined(QB_L) || !defined(QB_KGROUP)
-#error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..6>"
+#error "compile with -DQB_L=<number of 32-bit limbs> -DQB_KGROUP=<0..7>"
 #endif
 #include <cstdlib>
-#if (QB_KGROUP == 1 || QB_KGROUP == 2) && !defined(QB_COLD_COPY)
+#if (QB_KGROUP == 1 || QB_KGROUP == 2 || QB_KGROUP == 7) && !defined(QB_COLD_COPY)
 #define QB_COLD_COPY 1  // see fastops.cuh, "cold paths": measured per group -- on for k_series (-19 %) and k_scale (-2 %), off elsewhere
 #endif
 #if QB_KGROUP == 0
@@ -19,6 +20,8 @@
 #include "kernels_g3.cuh"
 #elif QB_KGROUP == 4
 #include "kernels_g4.cuh"
+#elif QB_KGROUP == 7
+#include "kernels_g7.cuh"
 #else
 #include "kernels_g5.cuh"
 #endif
@@ -65,8 +68,15 @@ namespace qb
 			cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
 			return n;
 		}();
-		// at most one small CTA per SM: the small-CTA kernel (one warp per scheduler); otherwise the large lockstep CTAs
-		if (n_jobs <= sms * QB_SERIES_THREADS_SMALL)
+		// a batch that fits the cooperative kernel's single wave: eight warps per 32 jobs (kernels_g7.cuh); at most one small
+		// CTA per SM: the small-CTA kernel (one warp per scheduler); otherwise the large lockstep CTAs
+		// QB_SERIES_COOP: jobs per SM up to which the cooperative kernel runs (0 = never); read at every launch so that a test
+		// can run one batch through both kernels
+		const char* coop_env = std::getenv("QB_SERIES_COOP");
+		const int coop_limit = coop_env ? std::atoi(coop_env) : 64;
+		if (n_jobs <= sms * coop_limit)
+			launch_series_coop<QB_L>(cx, n_jobs, delta, spin, b0, coef, coefx, b, st);
+		else if (n_jobs <= sms * QB_SERIES_THREADS_SMALL)
 			k_series<QB_L, QB_SERIES_THREADS_SMALL><<<(n_jobs + QB_SERIES_THREADS_SMALL - 1) / QB_SERIES_THREADS_SMALL, QB_SERIES_THREADS_SMALL,
 			                                         series_smem_bytes<QB_L, QB_SERIES_THREADS_SMALL>(), st>>>(cx, n_jobs, delta, spin, b0, coef, coefx, b);
 		else
@@ -162,6 +172,19 @@ namespace qb
 		k_dec_gather<<<unsigned((n * 32 + threads - 1) / threads), threads, 0, st>>>(n, slots, slot, len, ofs, text);
 	}
 #endif
+#elif QB_KGROUP == 7
+	template <>
+	void launch_series_coop<QB_L>(const DevCtx& cx, int n_jobs, const mpf<QB_L>* delta, const uint32_t* spin, const mpf<QB_L>* b0,
+	                              const mpf<QB_L>* coef, const uint32_t* coefx, mpf<QB_L>* b, cudaStream_t st)
+	{
+		static const bool attr_set = [] {
+			cudaFuncSetAttribute(k_series_coop<QB_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(CoopSmem<QB_L>::bytes));
+			return true;
+		}();
+		(void)attr_set;
+		k_series_coop<QB_L><<<(n_jobs + QB_COOP_JOBS - 1) / QB_COOP_JOBS, QB_COOP_T, CoopSmem<QB_L>::bytes, st>>>(cx, n_jobs, delta, spin, b0,
+		                                                                                                          coef, coefx, b);
+	}
 #elif QB_KGROUP == 6
 	template <>
 	void launch_horner<QB_L>(const DevCtx& cx, int n_tables, const mpf<QB_L>* a, const mpf<QB_L>* pw, mpf<QB_L>* fr,

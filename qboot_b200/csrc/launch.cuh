@@ -83,6 +83,9 @@ namespace qb
 	void launch_series(const DevCtx& cx, int n_jobs, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* b0,
 	                   const mpf<L>* coef, const uint32_t* coefx, mpf<L>* b, cudaStream_t st);
 	template <int L>
+	void launch_series_coop(const DevCtx& cx, int n_jobs, const mpf<L>* delta, const uint32_t* spin, const mpf<L>* b0,
+	                        const mpf<L>* coef, const uint32_t* coefx, mpf<L>* b, cudaStream_t st);
+	template <int L>
 	void launch_scale(const DevCtx& cx, int n_tables, const TableRef* tref, const mpf<L>* b, const mpf<L>* pw, mpf<L>* a,
 	                  cudaStream_t st);
 	template <int L>

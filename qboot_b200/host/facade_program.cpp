@@ -331,13 +331,17 @@ namespace qboot
 	{
 		throw std::logic_error("qboot_b200: get_spectrum (extremal functional method) is outside the scope of this engine");
 	}
+	// host half of the bilinear-bases batch for ONE scale factor, built on the host pool: the operands as records, ready to be
+	// concatenated into the device call
 	struct BilinearSamples
 	{
-		Vector<real> xs, s0, s1;  // sample points, sqrt(s_k), sqrt(s_k x_k)
+		uint32_t deg = 0;
+		vector<uint32_t> coef, xr, sr;  // coefficients of q_0 .. q_{deg/2}; x_k; sqrt(s_k), sqrt(s_k x_k) interleaved
+		vector<int32_t> ofs;            // coefficient range of q_m: [ofs[m], ofs[m + 1])
 	};
-	BilinearSamples prepare_bilinear_samples(const ScaleFactor& chi);
-	static vector<std::array<Matrix<real>, 2>> bilinear_at_samples_batch(b200::Engine& eng, const vector<const ScaleFactor*>& chis,
-	                                                                    const vector<const BilinearSamples*>& samples);
+	BilinearSamples prepare_bilinear_samples(const ScaleFactor& chi, size_t W);
+	static vector<std::array<Matrix<real>, 2>> bilinear_at_samples_batch(b200::Engine& eng, const vector<const BilinearSamples*>& samples,
+	                                                                    uint32_t parallel);
 	// src/bootstrap_equation.cpp:555-593, batched
 	PolynomialProgram BootstrapEquation::convert(const unique_ptr<SDPMode>& mode, uint32_t parallel, const unique_ptr<_event_base>& event) const
 	{
@@ -388,11 +392,12 @@ namespace qboot
 				}
 			});
 			vector<std::function<int()>> tasks;
+			const size_t W = plan.W;
 			for (auto& it : plan.items)
 				if (it.op_index >= 0 && it.scale)
-					tasks.emplace_back([&it] {
+					tasks.emplace_back([&it, W] {
 						it.scale->_finish_bases();
-						it.samples = std::make_shared<BilinearSamples>(prepare_bilinear_samples(*it.scale));
+						it.samples = std::make_shared<BilinearSamples>(prepare_bilinear_samples(*it.scale, W));
 						return 0;
 					});
 			try
@@ -411,15 +416,10 @@ namespace qboot
 		{
 			// the bases at the sample points: one more device batch (create_input's other half, src/polynomial_program.cpp:224-229)
 			_scoped_event scope("bilinear bases at the sample points (GPU)", event);
-			vector<const ScaleFactor*> chis;
 			vector<const BilinearSamples*> smp;
 			for (auto& it : plan.items)
-				if (it.op_index >= 0 && it.scale)
-				{
-					chis.push_back(it.scale.get());
-					smp.push_back(static_cast<const BilinearSamples*>(it.samples.get()));
-				}
-			auto bl = bilinear_at_samples_batch(*plan.engine, chis, smp);
+				if (it.op_index >= 0 && it.scale) smp.push_back(static_cast<const BilinearSamples*>(it.samples.get()));
+			auto bl = bilinear_at_samples_batch(*plan.engine, smp, std::max(parallel, cont_.parallel()));
 			size_t i = 0;
 			for (auto& it : plan.items)
 				if (it.op_index >= 0 && it.scale) it.bilinear = move(bl[i++]);
@@ -668,46 +668,64 @@ namespace qboot
 	// and the final product on the GPU; the square roots, 2 (D + 1) per constraint, stay on the host)
 	// host half of that batch, one scale factor at a time (thread-safe: run on the host pool): the sample points and the
 	// two square roots per point
-	BilinearSamples prepare_bilinear_samples(const ScaleFactor& chi)
+	BilinearSamples prepare_bilinear_samples(const ScaleFactor& chi, size_t W)
 	{
 		BilinearSamples in;
-		in.xs = chi.sample_points();
+		const auto put = [W](vector<uint32_t>& v, const real& r) { v.insert(v.end(), r._words(), r._words() + W); };
+		const auto xs = chi.sample_points();
 		const auto scs = chi.sample_scalings();
-		in.s0 = Vector<real>(in.xs.size());
-		in.s1 = Vector<real>(in.xs.size());
-		for (uint32_t k = 0; k < in.xs.size(); ++k)
+		const auto q = chi.bilinear_bases();
+		in.deg = chi.max_degree();
+		in.xr.reserve(W * xs.size());
+		in.sr.reserve(2 * W * xs.size());
+		for (uint32_t k = 0; k < xs.size(); ++k)
 		{
-			in.s0[k] = mp::sqrt(scs[k]);
-			in.s1[k] = mp::sqrt(scs[k] * in.xs[k]);
+			put(in.xr, xs[k]);
+			put(in.sr, mp::sqrt(scs[k]));
+			put(in.sr, mp::sqrt(scs[k] * xs[k]));
+		}
+		in.ofs.push_back(0);
+		for (uint32_t m = 0; m <= in.deg / 2; ++m)
+		{
+			for (int32_t p = 0; p <= q[m].degree(); ++p) put(in.coef, q[m].at(uint32_t(p)));
+			in.ofs.push_back(int32_t(in.coef.size() / W));
 		}
 		return in;
 	}
-	static vector<std::array<Matrix<real>, 2>> bilinear_at_samples_batch(b200::Engine& eng, const vector<const ScaleFactor*>& chis,
-	                                                                    const vector<const BilinearSamples*>& samples)
+	// the device batch over any number of prepared scale factors; concatenation and the call are serial (block copies), the
+	// results are turned into matrices on `parallel` host threads
+	static vector<std::array<Matrix<real>, 2>> bilinear_at_samples_batch(b200::Engine& eng, const vector<const BilinearSamples*>& samples,
+	                                                                    uint32_t parallel)
 	{
 		const size_t W = size_t(eng.words);
 		vector<int32_t> ofs{0};
 		vector<uint32_t> coef, xr, sr;
 		vector<qb_eval_item> items;
-		auto put = [W](vector<uint32_t>& v, const real& r) { v.insert(v.end(), r._words(), r._words() + W); };
-		for (size_t ci = 0; ci < chis.size(); ++ci)
+		vector<size_t> first(samples.size());  // first result of each scale factor
 		{
-			const ScaleFactor* chi = chis[ci];
+			size_t nc = 0, nx = 0, ni = 0;
+			for (const BilinearSamples* in : samples)
+			{
+				nc += in->coef.size();
+				nx += in->xr.size();
+				const size_t d0 = in->deg / 2, d1 = in->deg == 0 ? 0 : (in->deg - 1) / 2;
+				ni += (d0 + 1 + d1 + 1) * (size_t(in->deg) + 1);
+			}
+			coef.reserve(nc);
+			xr.reserve(nx);
+			sr.reserve(2 * nx);
+			items.reserve(ni);
+		}
+		for (size_t ci = 0; ci < samples.size(); ++ci)
+		{
 			const BilinearSamples& in = *samples[ci];
-			const uint32_t deg = chi->max_degree(), d0 = deg / 2, d1 = deg == 0 ? 0 : (deg - 1) / 2;
-			const auto q = chi->bilinear_bases();
-			const int32_t pb = int32_t(ofs.size()) - 1, xb = int32_t(xr.size() / W), sb = int32_t(sr.size() / W);
-			for (uint32_t m = 0; m <= d0; ++m)
-			{
-				for (int32_t p = 0; p <= q[m].degree(); ++p) put(coef, q[m].at(uint32_t(p)));
-				ofs.push_back(int32_t(coef.size() / W));
-			}
-			for (uint32_t k = 0; k <= deg; ++k)
-			{
-				put(xr, in.xs[k]);
-				put(sr, in.s0[k]);
-				put(sr, in.s1[k]);
-			}
+			const uint32_t deg = in.deg, d0 = deg / 2, d1 = deg == 0 ? 0 : (deg - 1) / 2;
+			const int32_t pb = int32_t(ofs.size()) - 1, cb = int32_t(coef.size() / W), xb = int32_t(xr.size() / W), sb = int32_t(sr.size() / W);
+			coef.insert(coef.end(), in.coef.begin(), in.coef.end());
+			xr.insert(xr.end(), in.xr.begin(), in.xr.end());
+			sr.insert(sr.end(), in.sr.begin(), in.sr.end());
+			for (size_t m = 1; m < in.ofs.size(); ++m) ofs.push_back(cb + in.ofs[m]);
+			first[ci] = items.size();
 			for (uint32_t m = 0; m <= d0; ++m)
 				for (uint32_t k = 0; k <= deg; ++k) items.push_back(qb_eval_item{pb + int32_t(m), xb + int32_t(k), sb + 2 * int32_t(k)});
 			for (uint32_t m = 0; m <= d1; ++m)
@@ -721,19 +739,21 @@ namespace qboot
 			                             sr.data(), int(items.size()), items.data(), out.data()),
 			          "qb_poly_eval_batch");
 		}
-		vector<std::array<Matrix<real>, 2>> res;
-		res.reserve(chis.size());
-		size_t pos = 0;
-		for (const ScaleFactor* chi : chis)
-		{
-			const uint32_t deg = chi->max_degree(), d0 = deg / 2, d1 = deg == 0 ? 0 : (deg - 1) / 2;
-			Matrix<real> q0(d0 + 1, deg + 1), q1(d1 + 1, deg + 1);
-			for (uint32_t m = 0; m <= d0; ++m)
-				for (uint32_t k = 0; k <= deg; ++k, ++pos) std::memcpy(q0.at(m, k)._words(), out.data() + W * pos, 4 * W);
-			for (uint32_t m = 0; m <= d1; ++m)
-				for (uint32_t k = 0; k <= deg; ++k, ++pos) std::memcpy(q1.at(m, k)._words(), out.data() + W * pos, 4 * W);
-			res.push_back({move(q0), move(q1)});
-		}
+		vector<std::array<Matrix<real>, 2>> res(samples.size());
+		vector<std::function<int()>> tasks;
+		for (size_t ci = 0; ci < samples.size(); ++ci)
+			tasks.emplace_back([&, ci] {
+				const uint32_t deg = samples[ci]->deg, d0 = deg / 2, d1 = deg == 0 ? 0 : (deg - 1) / 2;
+				size_t pos = first[ci];
+				Matrix<real> q0(d0 + 1, deg + 1), q1(d1 + 1, deg + 1);
+				for (uint32_t m = 0; m <= d0; ++m)
+					for (uint32_t k = 0; k <= deg; ++k, ++pos) std::memcpy(q0.at(m, k)._words(), out.data() + W * pos, 4 * W);
+				for (uint32_t m = 0; m <= d1; ++m)
+					for (uint32_t k = 0; k <= deg; ++k, ++pos) std::memcpy(q1.at(m, k)._words(), out.data() + W * pos, 4 * W);
+				res[ci] = {move(q0), move(q1)};
+				return 0;
+			});
+		_parallel_evaluate(tasks, std::max(1u, parallel));
 		return res;
 	}
 	// src/polynomial_program.cpp:152-232 -- the per-inequality loops run as ONE pack kernel over all blocks
@@ -814,14 +834,14 @@ namespace qboot
 			vector<BilinearSamples> prepared(chis.size());
 			vector<std::function<int()>> prep;
 			for (size_t i = 0; i < chis.size(); ++i)
-				prep.emplace_back([&prepared, &chis, i] {
-					prepared[i] = prepare_bilinear_samples(*chis[i]);
+				prep.emplace_back([&prepared, &chis, i, W] {
+					prepared[i] = prepare_bilinear_samples(*chis[i], W);
 					return 0;
 				});
 			_parallel_evaluate(prep, parallel);
 			vector<const BilinearSamples*> smp;
 			for (const auto& x : prepared) smp.push_back(&x);
-			auto bl = bilinear_at_samples_batch(*eng, chis, smp);
+			auto bl = bilinear_at_samples_batch(*eng, smp, parallel);
 			for (size_t i = 0; i < which.size(); ++i) ineqs_[which[i]]->bilinear_ = move(bl[i]);
 		}
 		vector<std::function<int()>> tasks;

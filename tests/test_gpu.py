@@ -225,6 +225,29 @@ def test_chunked_streams_match_single_chunk(tmp_path):
     assert np.array_equal(out["g2"], want)
 
 
+def test_series_kernels_agree(ref, monkeypatch):
+    """The series recurrence has two kernels: one thread per job (k_series) and, for the batches of a single PMP, eight warps
+    per 32 jobs (k_series_coop: products and polynomials off the chain).  QB_SERIES_COOP (read at every launch) chooses; the
+    same batch through both must give the same tables bit for bit, equal to the reference's -- special operators, zero S / P
+    (products with a zero operand leave the frame hand-over) and both recurrence lengths (spin 0 / spin > 0) included."""
+    prec, n_max, lam, n = 1024, 150, 9, 320
+    rng = random.Random(77)
+    spin, delta, S, P = _random_inputs(rng, prec, n)
+    for i, (sp, d) in enumerate([(0, "0"), (0, "1/2"), (2, "3"), (1, "2"), (0, "1"), (3, "4")]):
+        spin[i] = sp
+        delta[i] = qb.from_str(d, prec)
+    eng = _engine(prec, n_max, lam)
+    monkeypatch.setenv("QB_SERIES_COOP", "0")
+    per_thread = eng.gblock(spin, delta, S, P)
+    monkeypatch.setenv("QB_SERIES_COOP", "64")
+    coop = eng.gblock(spin, delta, S, P)
+    eng.close()
+    assert np.array_equal(per_thread, coop)
+    want = ref.gblock(prec, n_max, lam, "3", delta, spin, S, P)
+    bad = [i for i in range(n) if not same_records(want[i], coop[i])]
+    assert not bad, bad
+
+
 def test_sink_receives_the_tables_of_every_run():
     """qb_gblock_set_sink: every finished chunk of a run is copied to the sink (here page-locked host memory; in a multi-GPU
     job a peer GPU's buffer opened with qb_ipc_open) and the handle's stream joins the copies"""
