@@ -76,6 +76,8 @@ namespace qb
 
 #ifdef QB_L
 // ------------------------------------------------------------------------------------------------------------------
+#include <chrono>
+#include <cstdio>
 #include <thread>
 #include "hostmath.hpp"
 #include "block.cuh"
@@ -170,6 +172,10 @@ namespace qb
 		std::vector<cudaEvent_t> dep_ev;         // one per front group + two per chunk
 		cudaEvent_t fork_ev = nullptr, copy_done_ev = nullptr, fin_done_ev = nullptr, lo_done_ev = nullptr;
 		cudaStream_t copy_stream = nullptr;      // device -> host copies of finished chunks (fetch_dst)
+		// side stream of a single-chunk run (one PMP): work that does not depend on the series recurrence -- the powers of
+		// rho, the v^d tables of the assembly -- runs beside k_series, which leaves most SMs idle at that size
+		cudaStream_t aux_stream = nullptr;
+		cudaEvent_t aux_fork_ev = nullptr, aux_done_ev = nullptr;
 		std::vector<int> job_of_table;  // first job of every table (+ sentinel)
 		std::vector<int> chunk_t;       // table boundaries of the chunks
 		int n_chunks = 1, sm_count = 0;
@@ -190,9 +196,9 @@ namespace qb
 			pmp_release();
 			for (cudaEvent_t e_ : ev) cudaEventDestroy(e_);
 			for (cudaEvent_t e_ : dep_ev) cudaEventDestroy(e_);
-			for (cudaEvent_t e_ : {fork_ev, copy_done_ev, fin_done_ev, lo_done_ev})
+			for (cudaEvent_t e_ : {fork_ev, copy_done_ev, fin_done_ev, lo_done_ev, aux_fork_ev, aux_done_ev})
 				if (e_) cudaEventDestroy(e_);
-			for (cudaStream_t s_ : {lo_stream, mid_stream, fin_stream, copy_stream})
+			for (cudaStream_t s_ : {lo_stream, mid_stream, fin_stream, copy_stream, aux_stream})
 				if (s_) cudaStreamDestroy(s_);
 			if (stream) cudaStreamDestroy(stream);
 		}
@@ -219,6 +225,14 @@ namespace qb
 		if (e_ != cudaSuccess) return fail(e_, #call); \
 	} while (0)
 
+		int ensure_aux()
+		{
+			if (aux_stream) return 0;
+			QB_CU(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+			QB_CU(cudaEventCreateWithFlags(&aux_fork_ev, cudaEventDisableTiming));
+			QB_CU(cudaEventCreateWithFlags(&aux_done_ev, cudaEventDisableTiming));
+			return 0;
+		}
 		int context_init(uint32_t nmax, uint32_t lam, int64_t en, uint32_t ed) override
 		{
 			if (ed == 0 || lam > 200 || nmax == 0) return -4;
@@ -240,9 +254,10 @@ namespace qb
 			has_ctx = false;
 			n_max = nmax;
 			lambda = lam;
+			// b[0] depends on (spin, epsilon) only: a scan that builds one Context per PMP keeps the values
+			if (eps.num != en || eps.den != ed) b0_cache.clear();
 			eps = Rational{en, ed};
 			make_context_consts<L>(consts, lam, prec);
-			b0_cache.clear();
 			// upload: rho | mat | kfact | ln2e | ln4e | lnrhoe
 			size_t n1 = size_t(lam) + 1;
 			constexpr int E2 = ContextConsts<L>::E2;
@@ -393,6 +408,15 @@ namespace qb
 			if (!has_ctx) return -3;
 			if (n < 0 || (n > 0 && (!spin || !delta || !S || !P))) return -4;
 			QB_CU(cudaSetDevice(device));
+			// QB_PLAN_TRACE=1: where the planner's host time goes (stderr)
+			static const bool plan_trace = std::getenv("QB_PLAN_TRACE") != nullptr;
+			auto t_last = std::chrono::steady_clock::now();
+			auto lap = [&](const char* what) {
+				if (!plan_trace) return;
+				const auto t = std::chrono::steady_clock::now();
+				std::fprintf(stderr, "[qb plan] %-24s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+				t_last = t;
+			};
 			const T* hd = reinterpret_cast<const T*>(delta);
 			const T* hS = reinterpret_cast<const T*>(S);
 			const T* hP = reinterpret_cast<const T*>(P);
@@ -423,6 +447,7 @@ namespace qb
 						if (int rc = leading_coefficient(b0tab[spin[t]], spin[t])) return rc;
 					}
 			}
+			lap("b[0] by spin");
 			// the divergence test is the only per-table arithmetic of the planner: fan it out over host threads
 			std::vector<uint8_t> diverges(static_cast<size_t>(n), 0);
 			bool any_divergent = false;
@@ -437,6 +462,7 @@ namespace qb
 				for (auto& th : pool) th.join();
 				for (int t = 0; t < n && !any_divergent; ++t) any_divergent = diverges[size_t(t)] != 0;
 			}
+			lap("divergence tests");
 			// Common case, no divergent operator: job t IS table t -- the device-side job arrays alias the table arrays and
 			// nothing is repacked (for a scan-sized batch the repacking and its upload were ~0.1 s of host time per call).
 			if (!any_divergent)
@@ -512,6 +538,7 @@ namespace qb
 			for (int c = 0; c < n_chunks; ++c) max_chunk = std::max(max_chunk, chunk_t[size_t(c) + 1] - chunk_t[size_t(c)]);
 			a_slot_records = (size_t(lambda) + 1) * (size_t(n_max) + 1) * size_t(n_chunks > 1 ? max_chunk : n);
 			if (n == 0) return 0;
+			lap("jobs and chunks");
 			const size_t nt = size_t(n), nj = size_t(n_jobs), dimM = size_t(cf_dim(int(lambda))), n1 = size_t(lambda) + 1;
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || (any_divergent && d_jobs.ensure(sizeof(T) * 3 * nj + 4 * nj)) ||
 			    d_b0tab.ensure(sizeof(T) * b0tab.size()) ||
@@ -520,6 +547,7 @@ namespace qb
 			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (2 * n1 + 1) * nt) || d_qc.ensure(sizeof(T) * nt) || d_a.ensure(sizeof(T) * a_slot_records) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;
+			lap("device buffers");
 			t_delta = d_in.as<T>();
 			t_S = t_delta + nt;
 			t_P = t_S + nt;
@@ -549,6 +577,7 @@ namespace qb
 			QB_CU(cudaMemcpyAsync(d_b0tab.p, b0tab.data(), sizeof(T) * b0tab.size(), cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaMemcpyAsync(d_tref.p, tr.data(), sizeof(TableRef) * nt, cudaMemcpyHostToDevice, stream));
 			QB_CU(cudaStreamSynchronize(stream));  // host vectors go out of scope
+			lap("uploads");
 			n_tables = n;
 			return 0;
 		}
@@ -640,14 +669,24 @@ namespace qb
 			ev_stage.push_back(stage);
 			return 0;
 		}
-		int run_serial(cudaStream_t st)
+		// side: the powers go to the side stream (not while timing stages or debugging: one stream then)
+		int run_serial(cudaStream_t st, bool side)
 		{
 			ev_used = 0;
 			ev_stage.clear();
 			const int n_groups = int(group_c.size()) - 1;
+			if (side)
+				if (int rc_ = ensure_aux()) return rc_;
 			for (int g = 0; g < n_groups; ++g)
 			{
 				const Range R = group_range(g);
+				if (side)
+				{
+					QB_CU(cudaEventRecord(aux_fork_ev, st));
+					QB_CU(cudaStreamWaitEvent(aux_stream, aux_fork_ev, 0));
+					stage_pow(R, aux_stream);
+					QB_CU(cudaEventRecord(aux_done_ev, aux_stream));
+				}
 				if (int rc_ = tick(0, st)) return rc_;
 				stage_rec(R, st);
 				if (int rc_ = debug_sync("k_rec_coeffs")) return rc_;
@@ -655,7 +694,10 @@ namespace qb
 				stage_series(R, st);
 				if (int rc_ = debug_sync("k_series")) return rc_;
 				if (int rc_ = tick(2, st)) return rc_;
-				stage_pow(R, st);
+				if (side)
+					QB_CU(cudaStreamWaitEvent(st, aux_done_ev, 0));
+				else
+					stage_pow(R, st);
 				if (int rc_ = debug_sync("k_pow")) return rc_;
 				for (int c = group_c[size_t(g)]; c < group_c[size_t(g) + 1]; ++c)
 				{
@@ -681,7 +723,7 @@ namespace qb
 			static const bool serial_env = std::getenv("QB_DEBUG_SYNC") != nullptr || std::getenv("QB_SERIAL") != nullptr;
 			if (timing || n_chunks == 1 || serial_env)
 			{
-				if (int rc = run_serial(stream)) return rc;
+				if (int rc = run_serial(stream, !timing && !serial_env)) return rc;
 				QB_CU(cudaGetLastError());
 				tables_valid = true;
 				return 0;

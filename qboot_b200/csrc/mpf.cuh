@@ -222,6 +222,31 @@ namespace qb
 	template <int NA, int NB>
 	QB_HD QB_INLINE void mul_limbs(uint32_t* out, const uint32_t* a, const uint32_t* b)
 	{
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__) && defined(__BYTE_ORDER__) && __BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__
+		// host (planner, facade arithmetic): the same exact product on 64-bit limbs -- a quarter of the limb products
+		if (NA >= 4 && NB >= 4)
+		{
+			constexpr int A64 = (NA + 1) / 2, B64 = (NB + 1) / 2;
+			uint64_t x[A64], y[B64], z[A64 + B64];
+			for (int i = 0; i < A64; ++i) x[i] = uint64_t(a[2 * i]) | (2 * i + 1 < NA ? uint64_t(a[2 * i + 1]) << 32 : 0);
+			for (int i = 0; i < B64; ++i) y[i] = uint64_t(b[2 * i]) | (2 * i + 1 < NB ? uint64_t(b[2 * i + 1]) << 32 : 0);
+			for (int k = 0; k < A64 + B64; ++k) z[k] = 0;
+			for (int i = 0; i < A64; ++i)
+			{
+				uint64_t carry = 0;
+				const uint64_t xi = x[i];
+				for (int j = 0; j < B64; ++j)
+				{
+					const unsigned __int128 t = (unsigned __int128)xi * y[j] + z[i + j] + carry;
+					z[i + j] = uint64_t(t);
+					carry = uint64_t(t >> 64);
+				}
+				z[i + B64] = carry;
+			}
+			for (int k = 0; k < NA + NB; ++k) out[k] = uint32_t(z[k >> 1] >> (32 * (k & 1)));
+			return;
+		}
+#endif
 		uint32_t rb[NB], acc[NB];
 #pragma unroll
 		for (int j = 0; j < NB; ++j)
@@ -928,6 +953,91 @@ namespace qb
 			QB_ROLL
 			for (int i = 0; i < L; ++i) R[i] = a.m[i];
 		R[L] = 0u;
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__) && defined(__BYTE_ORDER__) && __BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__
+		// host (facade arithmetic, planner): the same quotient by Knuth D on 64-bit limbs.  U = (R 2^32 + nextlimb) 2^(32 (L + 1))
+		// is divided by V = D (even L) or D 2^32 (odd L: keeps V normalised); for even L that is one 32-bit limb more of
+		// quotient than needed, which joins the sticky bit.
+		if (L >= 4)
+		{
+			constexpr int NV = (L + 1) / 2, NU = L + 1, NQ = NU - NV + 1;
+			uint64_t V[NV], U[NU + 1], QQ[NQ];
+			{
+				uint32_t v32[2 * NV], u32[2 * NU];
+				for (int i = 0; i < 2 * NV; ++i) v32[i] = 0u;
+				for (int i = 0; i < L; ++i) v32[i + (L & 1)] = D[i];
+				for (int i = 0; i < 2 * NU; ++i) u32[i] = 0u;
+				u32[L + 1] = nextlimb;
+				for (int i = 0; i < L; ++i) u32[L + 2 + i] = R[i];
+				for (int i = 0; i < NV; ++i) V[i] = uint64_t(v32[2 * i]) | (uint64_t(v32[2 * i + 1]) << 32);
+				for (int i = 0; i < NU; ++i) U[i] = uint64_t(u32[2 * i]) | (uint64_t(u32[2 * i + 1]) << 32);
+				U[NU] = 0;
+			}
+			const uint64_t v1 = V[NV - 1], v0 = NV >= 2 ? V[NV - 2] : 0;
+			for (int j = NQ - 1; j >= 0; --j)
+			{
+				// quotient digit from U[j + NV], U[j + NV - 1], U[j + NV - 2] and v1, v0
+				const uint64_t u2 = U[j + NV], u1 = U[j + NV - 1], u0 = j + NV >= 2 ? U[j + NV - 2] : 0;
+				unsigned __int128 qhat, rhat;
+				if (u2 >= v1)
+				{
+					qhat = ~uint64_t(0);
+					rhat = (((unsigned __int128)u2 << 64) | u1) - qhat * v1;
+				}
+				else
+				{
+					const unsigned __int128 num = ((unsigned __int128)u2 << 64) | u1;
+					qhat = num / v1;
+					rhat = num - qhat * v1;
+				}
+				while ((rhat >> 64) == 0 && qhat * v0 > ((rhat << 64) | u0))
+				{
+					qhat -= 1;
+					rhat += v1;
+				}
+				uint64_t q = uint64_t(qhat), borrow = 0, carry = 0;
+				for (int i = 0; i < NV; ++i)
+				{
+					const unsigned __int128 p = (unsigned __int128)q * V[i] + carry;
+					carry = uint64_t(p >> 64);
+					const uint64_t lo = uint64_t(p), cur = U[j + i], d1_ = cur - lo;
+					const uint64_t b1 = cur < lo;
+					U[j + i] = d1_ - borrow;
+					borrow = b1 | (d1_ < borrow);
+				}
+				{
+					const uint64_t cur = U[j + NV], d1_ = cur - carry;
+					const uint64_t b1 = cur < carry;
+					U[j + NV] = d1_ - borrow;
+					borrow = b1 | (d1_ < borrow);
+				}
+				if (borrow)
+				{
+					q -= 1;
+					uint64_t c = 0;
+					for (int i = 0; i < NV; ++i)
+					{
+						const unsigned __int128 t = (unsigned __int128)U[j + i] + V[i] + c;
+						U[j + i] = uint64_t(t);
+						c = uint64_t(t >> 64);
+					}
+					U[j + NV] += c;
+				}
+				QQ[j] = q;
+			}
+			uint64_t rem = 0;
+			for (int i = 0; i < NV; ++i) rem |= U[i];
+			uint32_t st = rem != 0;
+			if (L & 1)
+				for (int i = 0; i <= L; ++i) Q[i] = uint32_t(QQ[i >> 1] >> (32 * (i & 1)));
+			else
+			{
+				st |= uint32_t(QQ[0]) != 0u;
+				for (int i = 0; i <= L; ++i) Q[i] = uint32_t(QQ[(i + 1) >> 1] >> (32 * ((i + 1) & 1)));
+			}
+			round_to<L, L + 1>(r, sgn, e, Q, st, prec);
+			return;
+		}
+#endif
 		const uint32_t d1 = D[L - 1];
 		const uint32_t d0 = (L >= 2) ? D[L - 2] : 0u;
 		QB_ROLL

@@ -214,7 +214,7 @@ namespace qboot
 			}
 		}
 		// tables once each, then all blocks: leaves the values in the engine's arena (block i of the arena = items[i])
-		void run()
+		void run(const unique_ptr<_event_base>& event = {})
 		{
 			std::lock_guard<std::recursive_mutex> g(engine->mu);
 			vector<int32_t> eq_dim, eq_sym;
@@ -223,8 +223,15 @@ namespace qboot
 				eq_dim.push_back(int32_t(eq.dimension()));
 				eq_sym.push_back(int32_t(eq.symmetry()));
 			}
-			engine->check(qb_gblock_plan(engine->h, keys.size(), keys.spin.data(), keys.delta.data(), keys.S.data(), keys.P.data()), "qb_gblock_plan");
-			engine->check(qb_gblock_run(engine->h), "qb_gblock_run");
+			{
+				_scoped_event scope("  gblock plan", event);
+				engine->check(qb_gblock_plan(engine->h, keys.size(), keys.spin.data(), keys.delta.data(), keys.S.data(), keys.P.data()), "qb_gblock_plan");
+			}
+			{
+				_scoped_event scope("  gblock run", event);
+				engine->check(qb_gblock_run(engine->h), "qb_gblock_run");
+			}
+			_scoped_event scope("  pmp assemble", event);
 			engine->check(qb_pmp_assemble(engine->h, int(eq_dim.size()), eq_dim.data(), eq_sym.data(), int(blocks.size()), blocks.data(),
 			                              int(terms.size()), terms.data(), int(tab.size()), tab.data(), dvals.size(), dvals.words.data(),
 			                              coefs.size(), coefs.words.data()),
@@ -384,7 +391,7 @@ namespace qboot
 				try
 				{
 					_scoped_event inner("tables + assembly (GPU)", event);
-					plan.run();
+					plan.run(event);
 				}
 				catch (...)
 				{
