@@ -543,7 +543,7 @@ namespace qb
 			if (d_in.ensure(sizeof(T) * 3 * nt + 4 * nt) || (any_divergent && d_jobs.ensure(sizeof(T) * 3 * nj + 4 * nj)) ||
 			    d_b0tab.ensure(sizeof(T) * b0tab.size()) ||
 			    d_tref.ensure(sizeof(TableRef) * nt) || d_coef.ensure(sizeof(T) * QB_NCOEF * nj) ||
-			    d_coefx.ensure(4 * size_t(fx_words<L>()) * QB_NCOEF * nj) ||
+			    d_coefx.ensure(4 * size_t(fx_words<L>()) * QB_NCOEF * (nj + 32))  /* blocks of 32 jobs per launch: the last one may be partial */ ||
 			    d_b.ensure(sizeof(T) * (size_t(n_max) + 1) * nj) || d_fr.ensure(sizeof(T) * n1 * nt) || d_pw.ensure(sizeof(T) * (2 * n1 + 1) * nt) || d_qc.ensure(sizeof(T) * nt) || d_a.ensure(sizeof(T) * a_slot_records) ||
 			    d_g.ensure(sizeof(T) * dimM * nt))
 				return -7;

@@ -73,13 +73,13 @@ namespace qb
 			coef_load(c, cw, i * st + d, job, n_jobs);
 			uint32_t V[W], sg;
 			ok = fx::from_record<L>(V, sg, c, E) && ok;
-			uint32_t* q = coefx + size_t(i * st + d) * FW * size_t(n_jobs) + job;
+			uint32_t* q = coefx + coefx_offset<L>(job, i * st + d);
 			q[0] = sg;
-			q[size_t(n_jobs)] = uint32_t(E);
-			for (int j = 0; j < W; ++j) q[size_t(2 + j) * size_t(n_jobs)] = V[j];
+			q[32] = uint32_t(E);
+			for (int j = 0; j < W; ++j) q[(2 + j) * 32] = V[j];
 		}
 		// the verdict goes into the leading coefficient's header
-		coefx[size_t(i * st + deg) * FW * size_t(n_jobs) + job] |= ok ? 1u : 0u;
+		coefx[coefx_offset<L>(job, i * st + deg)] |= ok ? 1u : 0u;
 	}
 
 	// The series recurrence b[n] = -(sum_{i=1}^{min(n,K-1)} p_i(n) b[n-i]) / p_0(n)       (src/hor_recursion.cpp:31-37),
@@ -181,30 +181,29 @@ namespace qb
 				bool fixed = false;
 				{
 					constexpr int W = L + 2, FW = fx_words<L>();
-					const size_t cstride = size_t(FW) * size_t(n_jobs);
+					constexpr int CS = FW * 32;  // words from one coefficient to the next
 					// The coefficients (5.8 KB per job) stream from DRAM at every step -- the jobs in flight hold 300 MB of
 					// them.  Each lane touches one line of the NEXT polynomial's coefficients now, a polynomial ahead of their use
-					// (the lanes of a warp read the same lines: word-planar layout), so that the loads below find them in L2.
+					// (the lanes of a warp read the same lines: block layout, launch.cuh), so that the loads below find them in L2.
 					{
 						const int ipn = divisor ? 1 : (i + 1 < K ? i + 1 : 0);
-						const uint32_t* nb = coefx + size_t(ipn * st) * cstride + (cj & ~31);
+						const uint32_t* nb = coefx + coefx_offset<L>(cj & ~31, ipn * st);
 						QB_ROLL
-						for (int idx = int(threadIdx.x & 31u); idx < st * FW; idx += 32)
-							asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + size_t(idx) * size_t(n_jobs)));
+						for (int idx = int(threadIdx.x & 31u); idx < st * FW; idx += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + idx * 32));
 					}
-					const uint32_t* q = coefx + size_t(ip * st + deg) * cstride + cj;
+					const uint32_t* q = coefx + coefx_offset<L>(cj, ip * st + deg);
 					uint32_t sg = q[0];
 					if (sg & 1u)
 					{
-						const int32_t E = int32_t(q[size_t(n_jobs)]);
+						const int32_t E = int32_t(q[32]);
 						uint32_t V[W], C[W], Cn[W], csgn;
 #pragma unroll
-						for (int j = 0; j < W; ++j) V[j] = q[size_t(2 + j) * size_t(n_jobs)];
+						for (int j = 0; j < W; ++j) V[j] = q[(2 + j) * 32];
 						// software pipeline: the coefficient of the next Horner step is in flight while this one is computed
-						q -= cstride;
+						q -= CS;
 						csgn = q[0];
 #pragma unroll
-						for (int j = 0; j < W; ++j) Cn[j] = q[size_t(2 + j) * size_t(n_jobs)];
+						for (int j = 0; j < W; ++j) Cn[j] = q[(2 + j) * 32];
 						fixed = true;
 						QB_ROLL
 						for (int d = deg - 1; d >= 0; --d)
@@ -214,10 +213,10 @@ namespace qb
 							for (int j = 0; j < W; ++j) C[j] = Cn[j];
 							if (d > 0)
 							{
-								q -= cstride;
+								q -= CS;
 								csgn = q[0];
 #pragma unroll
-								for (int j = 0; j < W; ++j) Cn[j] = q[size_t(2 + j) * size_t(n_jobs)];
+								for (int j = 0; j < W; ++j) Cn[j] = q[(2 + j) * 32];
 							}
 							if (fixed) fixed = fx::horner_step<L>(V, sg, n, C, csg, prec);
 						}

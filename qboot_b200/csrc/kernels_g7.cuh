@@ -45,26 +45,25 @@ namespace qb
 	__device__ __forceinline__ void coop_poly(mpf<L>& p, uint32_t n, int ip, int deg, int cj, int n_jobs, const uint32_t* __restrict__ cw,
 	                                          const uint32_t* __restrict__ coefx, int prec)
 	{
-		constexpr int W = L + 2, FW = fx_words<L>();
+		constexpr int W = L + 2, CS = fx_words<L>() * 32;
 		const int st = deg + 1;
-		const size_t cstride = size_t(FW) * size_t(n_jobs);
 		bool fixed = false;
-		const uint32_t* q = coefx + size_t(ip * st + deg) * cstride + cj;
+		const uint32_t* q = coefx + coefx_offset<L>(cj, ip * st + deg);
 		uint32_t sg = q[0];
 		if (sg & 1u)
 		{
-			const int32_t E = int32_t(q[size_t(n_jobs)]);
+			const int32_t E = int32_t(q[32]);
 			uint32_t V[W], C[W];
 #pragma unroll
-			for (int j = 0; j < W; ++j) V[j] = q[size_t(2 + j) * size_t(n_jobs)];
+			for (int j = 0; j < W; ++j) V[j] = q[(2 + j) * 32];
 			fixed = true;
 			QB_ROLL
 			for (int d = deg - 1; d >= 0; --d)
 			{
-				q -= cstride;
+				q -= CS;
 				const uint32_t csg = q[0];
 #pragma unroll
-				for (int j = 0; j < W; ++j) C[j] = q[size_t(2 + j) * size_t(n_jobs)];
+				for (int j = 0; j < W; ++j) C[j] = q[(2 + j) * 32];
 				if (fixed) fixed = fx::horner_step<L>(V, sg, n, C, csg, prec);
 			}
 			if (fixed) fixed = fx::to_record<L>(p, V, sg, E);

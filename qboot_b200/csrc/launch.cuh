@@ -77,6 +77,14 @@ namespace qb
 	{
 		return L + 4;
 	}
+	// Fixed-point copies of the recurrence coefficients (polyfx.cuh): blocks of 32 jobs, [block][coefficient][word][lane].
+	// The words of one coefficient are 128 bytes apart and the coefficients of a polynomial follow each other, so a thread
+	// walks a polynomial with compile-time offsets from one pointer, and a warp's access is one line.
+	template <int L>
+	QB_HD inline size_t coefx_offset(int job, int c)
+	{
+		return (size_t(job >> 5) * QB_NCOEF + size_t(c)) * size_t(fx_words<L>()) * 32 + size_t(job & 31);
+	}
 	template <int L>
 	void launch_coef_fx(const DevCtx& cx, int n_jobs, const uint32_t* spin, const mpf<L>* coef, uint32_t* coefx, cudaStream_t st);
 	template <int L>
