@@ -200,6 +200,7 @@ namespace qb
 #pragma unroll
 						for (int j = 0; j < W; ++j) V[j] = q[(2 + j) * 32];
 						// software pipeline: the coefficient of the next Horner step is in flight while this one is computed
+						// (without it the series stage is 3 % slower although the loop is 34 moves shorter)
 						q -= CS;
 						csgn = q[0];
 #pragma unroll

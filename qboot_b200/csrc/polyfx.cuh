@@ -144,15 +144,23 @@ namespace qb
 		{
 			constexpr int W = L + 2;
 			{
-				uint64_t cy = 0;
+				// V *= n: limb j of the result is lo(V[j] n) + hi(V[j-1] n) + carry -- one wide product and one add-with-carry
+				// per limb (an accumulating 64-bit product costs two register moves per limb on top)
+				uint64_t p = uint64_t(V[0]) * n;
+				V[0] = uint32_t(p);
+				uint32_t h = uint32_t(p >> 32);
+				p = uint64_t(V[1]) * n;
+				QB_CY_DECL
+				QB_ADD_FIRST(V[1], uint32_t(p), h);
+				h = uint32_t(p >> 32);
 #pragma unroll
-				for (int j = 0; j < W; ++j)
+				for (int j = 2; j < W; ++j)
 				{
-					cy += uint64_t(V[j]) * n;
-					V[j] = uint32_t(cy);
-					cy >>= 32;
+					p = uint64_t(V[j]) * n;
+					QB_ADD_NEXT(V[j], uint32_t(p), h);
+					h = uint32_t(p >> 32);
 				}
-				// cy == 0: the frame exponent bounds every intermediate
+				// no carry out of the top limb and h == 0: the frame exponent bounds every intermediate
 			}
 			if (!round_sig<L>(V, prec)) return false;
 			if (((sgn ^ csgn) & SIGN_BIT) == 0u)
