@@ -70,6 +70,44 @@ def test_primitives_vs_mpfr_live(hostemu, ref, prec):
     assert same_records(ref.op("sqrt", prec, a=pos), out)
 
 
+@pytest.mark.parametrize("prec", [128, 150, 256, 600, 608, 800, 1024, 1200, 1536])
+def test_division_quotient_digit_corrections(hostemu, ref, prec):
+    """Knuth's long division estimates every quotient digit from the top limbs and is occasionally one too large; the
+    multiply-subtract then borrows and the divisor is added back -- about once in 2^32 (2^64 on the host's 64-bit limbs)
+    for random operands, so random tests never see that branch.  Forced here: a divisor whose mantissa is 1000...0001 (or
+    1000...0 followed by a low tail) over numerators q * 1000...0 makes the estimate q while the digit is q - 1, in the
+    first digit and, through the shifted numerators, in later ones; also divisors of all ones (every estimate saturates)."""
+    L = (prec + 31) // 32
+    low = 1 << (32 * L - prec)  # lowest bit of a prec-bit mantissa inside its limbs
+    top = 1 << (32 * L - 1)
+
+    def rec(mant, exp=0, neg=False):
+        r = np.zeros(L + 2, dtype=np.uint32)
+        r[0] = 1 | (0x80000000 if neg else 0)
+        r[1] = np.uint32(exp & 0xFFFFFFFF)
+        for j in range(L):
+            r[2 + j] = (mant >> (32 * j)) & 0xFFFFFFFF
+        return r
+
+    divisors = [top | low, top | (low << 1) | low, top | (low << 40) | low, top | ((1 << 31) * low), (1 << (32 * L)) - low,
+                top | (((1 << 64) - 1) * low), top | (1 << (32 * L - 70))]
+    numerators = [top, top | low, top | (top >> 1), top | (top >> 33), top | (top >> 64), top | (top >> 65) | low,
+                  (1 << (32 * L)) - low, top | (low << 3)]
+    a, b = [], []
+    for d in divisors:
+        for nmr in numerators:
+            a.append(rec(nmr, 1))
+            b.append(rec(d, -3, neg=True))
+    a, b = np.stack(a), np.stack(b)
+    want = ref.op("div", prec, a=a, b=b)
+    assert same_records(want, emu_op(hostemu, "div", prec, a=a, b=b))
+    # ... and through the device's register-resident division (fastops.cuh: 3-by-2 reciprocal, add-back)
+    if prec in (608, 800, 1024, 1536):
+        assert same_records(want, _fast(hostemu, FAST["div"], prec, a=a, b=b))
+    want = ref.op("mul", prec, a=a, b=b)
+    assert same_records(want, emu_op(hostemu, "mul", prec, a=a, b=b))
+
+
 @pytest.mark.parametrize("prec", [600, 1024])
 def test_pow_vs_golden(hostemu, ref, prec):
     g = golden(f"ops_p{prec}")
