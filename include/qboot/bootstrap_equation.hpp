@@ -49,112 +49,81 @@ namespace qboot
 		explicit _pole_selector(uint32_t numax) : numax_(numax) {}
 		uint32_t operator()(uint32_t spin) const { return numax_ + std::min(numax_, spin) / 2; }
 	};
-	// coeff * ope[r] ope[c] * block
+	// One term of a crossing equation inside a sector: weight * ope[row] * ope[col] * block.
 	class Entry
 	{
-		uint32_t r_, c_;
-		mp::real coeff_;
-		Block block_;
+		struct Position
+		{
+			uint32_t row = 0, col = 0;
+		};
+		Position at_{};
+		mp::real weight_;
+		Block what_;
 
 	public:
+		// (row, col, weight, block); position (0, 0) and weight 1 when left out
+		Entry(uint32_t r, uint32_t c, const mp::real& coeff, const Block& block) : at_{r, c}, weight_(coeff), what_(block) {}
+		Entry(uint32_t r, uint32_t c, const Block& block) : at_{r, c}, weight_(1), what_(block) {}
+		Entry(const mp::real& coeff, const Block& block) : weight_(coeff), what_(block) {}
+		explicit Entry(const Block& block) : weight_(1), what_(block) {}
 		void _reset() &&
 		{
-			r_ = c_ = 0;
-			std::move(coeff_)._reset();
-			std::visit([](auto&& v) { std::move(v)._reset(); }, std::move(block_));
+			at_ = {};
+			std::move(weight_)._reset();
+			std::visit([](auto&& alt) { std::move(alt)._reset(); }, std::move(what_));
 		}
-		Entry(uint32_t r, uint32_t c, const mp::real& coeff, const Block& block) : r_(r), c_(c), coeff_(coeff), block_(block) {}
-		Entry(const mp::real& coeff, const Block& block) : Entry(0, 0, coeff, block) {}
-		Entry(uint32_t r, uint32_t c, const Block& block) : Entry(r, c, mp::real(1), block) {}
-		explicit Entry(const Block& block) : Entry(0, 0, mp::real(1), block) {}
-		[[nodiscard]] const Block& block() const { return block_; }
-		[[nodiscard]] uint32_t row() const { return r_; }
-		[[nodiscard]] uint32_t column() const { return c_; }
-		[[nodiscard]] const mp::real& coeff() const { return coeff_; }
+		[[nodiscard]] uint32_t row() const { return at_.row; }
+		[[nodiscard]] uint32_t column() const { return at_.col; }
+		[[nodiscard]] const mp::real& coeff() const { return weight_; }
+		[[nodiscard]] const Block& block() const { return what_; }
 	};
 	enum class SectorType : bool
 	{
 		Continuous = false,
 		Discrete = true
 	};
-	// a set of operators sharing one sz x sz matrix of OPE coefficients
+	// A set of operators sharing one size x size matrix of OPE coefficients.  A continuous sector lists (spin, range)
+	// requests; they become GeneralPrimaryOperators when the BootstrapEquation that owns the sector knows epsilon and the
+	// rule for the number of poles.  Bodies that are not one-liners: qboot_b200/host/facade_program.cpp.
 	class Sector
 	{
 		friend class BootstrapEquation;
+		struct Request  // Delta in [from, to); absent from: the unitarity bound, absent to: unbounded
+		{
+			uint32_t spin;
+			std::optional<mp::real> from{}, to{};
+		};
 		std::string name_;
 		uint32_t sz_;
 		SectorType type_;
-		// (spin, lower bound, upper bound) as given; turned into operators once epsilon and the pole rule are known
-		std::vector<std::tuple<uint32_t, std::optional<mp::real>, std::optional<mp::real>>> op_args_{};
+		std::vector<Request> requested_{};
 		std::vector<GeneralPrimaryOperator> ops_{};
 		std::optional<algebra::Vector<mp::real>> ope_{};
-		void set_operators(const mp::rational& epsilon, const std::function<uint32_t(uint32_t)>& num_poles) &
-		{
-			assert(type_ == SectorType::Continuous);
-			ops_.clear();
-			for (const auto& [sp, lb, ub] : op_args_)
-			{
-				if (ub.has_value())
-					ops_.emplace_back(sp, num_poles(sp), epsilon, lb.value(), ub.value());
-				else if (lb.has_value())
-					ops_.emplace_back(sp, num_poles(sp), epsilon, lb.value());
-				else
-					ops_.emplace_back(sp, num_poles(sp), epsilon);
-			}
-		}
+		void request(Request&& r) &;
+		void set_operators(const mp::rational& epsilon, const std::function<uint32_t(uint32_t)>& num_poles) &;
 
 	public:
-		void _reset() &&
-		{
-			std::string{}.swap(name_);
-			sz_ = 0;
-			type_ = SectorType::Continuous;
-			op_args_.clear();
-			ops_.clear();
-			ope_.reset();
-		}
-		Sector(std::string_view name, uint32_t size, SectorType type = SectorType::Discrete) : name_(name), sz_(size), type_(type) { assert(sz_ > 0); }
+		Sector(std::string_view name, uint32_t size, SectorType type = SectorType::Discrete);
 		// a discrete sector whose OPE coefficients are known: contributes the number ope^t M ope
-		Sector(std::string_view name, uint32_t size, algebra::Vector<mp::real>&& ope)
-		    : name_(name), sz_(size), type_(SectorType::Discrete), ope_{std::move(ope)}
-		{
-			assert(ope_->size() == sz_ && sz_ > 0);
-		}
+		Sector(std::string_view name, uint32_t size, algebra::Vector<mp::real>&& ope);
 		~Sector() = default;
-		Sector(const Sector& s) : name_(s.name_), sz_(s.sz_), type_(s.type_), op_args_(s.op_args_), ops_(s.ops_)
-		{
-			if (s.ope_.has_value()) ope_ = s.ope_.value().clone();
-		}
 		Sector(Sector&&) = default;
-		Sector& operator=(const Sector& s)
-		{
-			if (this != &s) *this = Sector(s);
-			return *this;
-		}
 		Sector& operator=(Sector&&) = default;
+		Sector(const Sector& s);  // deep: the OPE vector is move-only and gets cloned
+		Sector& operator=(const Sector& s) { return this == &s ? *this : (*this = Sector(s)); }
+		void _reset() &&;
 		[[nodiscard]] const std::string& name() const { return name_; }
 		[[nodiscard]] uint32_t size() const { return sz_; }
 		[[nodiscard]] SectorType type() const { return type_; }
 		[[nodiscard]] bool is_matrix() const { return sz_ > 1 && !ope_.has_value(); }
 		[[nodiscard]] const std::optional<algebra::Vector<mp::real>>& ope() const { return ope_; }
 		[[nodiscard]] const std::vector<GeneralPrimaryOperator>& _operators() const { return ops_; }
-		void add_op(uint32_t spin) &  // Delta >= unitarity bound
+		// continuous sectors only: Delta >= unitarity bound; Delta >= lb; lb <= Delta < ub (an infinite ub means none)
+		void add_op(uint32_t spin) & { request(Request{spin}); }
+		void add_op(uint32_t spin, const mp::real& lb) & { request(Request{spin, lb}); }
+		void add_op(uint32_t spin, const mp::real& lb, const mp::real& ub) &
 		{
-			assert(type_ == SectorType::Continuous);
-			op_args_.emplace_back(spin, std::optional<mp::real>{}, std::optional<mp::real>{});
-		}
-		void add_op(uint32_t spin, const mp::real& lb) &  // Delta >= lb
-		{
-			assert(type_ == SectorType::Continuous);
-			op_args_.emplace_back(spin, lb, std::optional<mp::real>{});
-		}
-		void add_op(uint32_t spin, const mp::real& lb, const mp::real& ub) &  // lb <= Delta < ub
-		{
-			assert(type_ == SectorType::Continuous);
-			if (ub.isinf())
-				add_op(spin, lb);
-			else
-				op_args_.emplace_back(spin, lb, ub);
+			request(ub.isinf() ? Request{spin, lb} : Request{spin, lb, ub});
 		}
 	};
 	class BootstrapEquation;

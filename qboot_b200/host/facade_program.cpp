@@ -265,6 +265,47 @@ namespace qboot
 		}
 	};
 
+	// ---- Sector ---------------------------------------------------------------------------------------------------------------
+	Sector::Sector(std::string_view name, uint32_t size, SectorType type) : name_(name), sz_(size), type_(type) { assert(sz_ > 0); }
+	Sector::Sector(std::string_view name, uint32_t size, Vector<real>&& ope) : name_(name), sz_(size), type_(SectorType::Discrete), ope_{move(ope)}
+	{
+		assert(sz_ > 0 && ope_->size() == sz_);
+	}
+	Sector::Sector(const Sector& s) : name_(s.name_), sz_(s.sz_), type_(s.type_), requested_(s.requested_), ops_(s.ops_)
+	{
+		if (s.ope_) ope_ = s.ope_->clone();
+	}
+	void Sector::_reset() &&
+	{
+		name_ = std::string{};
+		sz_ = 0;
+		type_ = SectorType::Continuous;
+		requested_.clear();
+		ops_.clear();
+		ope_.reset();
+	}
+	void Sector::request(Request&& r) &
+	{
+		assert(type_ == SectorType::Continuous);
+		requested_.push_back(move(r));
+	}
+	// src/bootstrap_equation.hpp:64-76 in the reference: the requests become operators, in the order they were made
+	void Sector::set_operators(const mp::rational& epsilon, const std::function<uint32_t(uint32_t)>& num_poles) &
+	{
+		assert(type_ == SectorType::Continuous);
+		ops_.clear();
+		for (const Request& r : requested_)
+		{
+			const uint32_t poles = num_poles(r.spin);
+			if (!r.from)
+				ops_.emplace_back(r.spin, poles, epsilon);
+			else if (!r.to)
+				ops_.emplace_back(r.spin, poles, epsilon, *r.from);
+			else
+				ops_.emplace_back(r.spin, poles, epsilon, *r.from, *r.to);
+		}
+	}
+
 	void BootstrapEquation::finish() &
 	{
 		for (const auto& eq : eqs_) N_ += eq.dimension();
