@@ -13,9 +13,11 @@
 //   5. text      qb_pmp_text: decimal digits of d_B / d_c; the host writes the bytes to the files
 // Only the normalisation vectors (a few N-vectors), the bilinear bases and file I/O stay on the host.
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <numeric>
 #include <sstream>
 #include <thread>
@@ -1089,20 +1091,30 @@ namespace qboot
 		for (uint32_t j = 0; j < J; ++j)
 			if (slots_[j]->dev_) packed = slots_[j]->dev_;
 		// the device formats the large arrays while host threads write the small files (blocks, objectives, bilinear bases)
-		std::exception_ptr text_error;
-		std::thread text_thread;
-		if (packed)
-			text_thread = std::thread([&] {
-				try
-				{
-					_scoped_event scope("decimal text (GPU)", event);
-					packed->ensure_text(nd);
-				}
-				catch (...)
-				{
-					text_error = std::current_exception();
-				}
-			});
+		// One overlapped phase, three kinds of workers:
+		//   * the text thread: the device formats the large arrays (d_B, d_c of every constraint) -> text_ready;
+		//   * the host pool: blocks.0, objectives, the text of bilinear_bases.0 piece by piece (the device formats each piece's
+		//     numbers) -> piece_ready[i]; then the per-constraint files, which wait for text_ready;
+		//   * the writer thread: bilinear_bases.0 is ONE sequential file (a third of the single-correlator problem's text):
+		//     piece i is written as soon as it is ready, underneath the formatting of the later pieces.
+		std::mutex mu;
+		std::condition_variable cv;
+		bool text_ready = !packed, failed = false;
+		vector<char> piece_ready(J, 0);
+		const auto signal = [&](auto&& change) {
+			{
+				std::lock_guard<std::mutex> g(mu);
+				change();
+			}
+			cv.notify_all();
+		};
+		const auto wait_for = [&](auto&& ready) {
+			std::unique_lock<std::mutex> lk(mu);
+			cv.wait(lk, [&] { return failed || ready(); });
+			return !failed;
+		};
+		std::exception_ptr text_error, writer_error;
+		std::thread text_thread, writer_thread;
 		struct Joiner
 		{
 			std::thread& t;
@@ -1110,10 +1122,69 @@ namespace qboot
 			{
 				if (t.joinable()) t.join();
 			}
-		} joiner{text_thread};
+		};
+		if (packed)
+			text_thread = std::thread([&] {
+				try
+				{
+					_scoped_event scope("decimal text (GPU)", event);
+					packed->ensure_text(nd);
+					signal([&] { text_ready = true; });
+				}
+				catch (...)
+				{
+					text_error = std::current_exception();
+					signal([&] { failed = true; });
+				}
+			});
+		Joiner join_text{text_thread};
 		std::shared_ptr<b200::Engine> eng = packed ? packed->engine : std::make_shared<b200::Engine>(mp::_prec(), 1u, 1u, mp::rational(1, 2));
 		const size_t W = size_t(eng->words);
+		vector<std::string> bl_pieces(J);
+		writer_thread = std::thread([&] {
+			try
+			{
+				_scoped_event scope("write_bilinear_bases", event);
+				std::ofstream f(root / "bilinear_bases.0", std::ios::binary);
+				const std::string head = std::to_string(J) + "\n";
+				f.write(head.data(), std::streamsize(head.size()));
+				for (uint32_t i = 0; i < J; ++i)
+				{
+					if (!wait_for([&] { return piece_ready[i] != 0; })) return;
+					f.write(bl_pieces[i].data(), std::streamsize(bl_pieces[i].size()));
+					std::string().swap(bl_pieces[i]);
+				}
+				if (!f) throw std::runtime_error("qboot_b200: cannot write " + (root / "bilinear_bases.0").string());
+			}
+			catch (...)
+			{
+				writer_error = std::current_exception();
+				signal([&] { failed = true; });
+			}
+		});
+		Joiner join_writer{writer_thread};
 		vector<std::function<int()>> tasks;
+		for (uint32_t i = 0; i < J; ++i)
+			tasks.emplace_back([&, i] {
+				vector<uint32_t> recs;
+				for (const auto& m : slots_[i]->bilinear()) append_records(recs, m, W);
+				std::string text;
+				vector<size_t> ends;
+				b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, text, &ends);
+				std::string& out = bl_pieces[i];
+				out.reserve(text.size() + 64);
+				size_t pos = 0, num = 0;
+				for (const auto& m : slots_[i]->bilinear())
+				{
+					out += std::to_string(m.row()) + " " + std::to_string(m.column()) + "\n";
+					num += size_t(m.row()) * m.column();
+					const size_t end = num ? ends[num - 1] : 0;
+					out.append(text, pos, end - pos);
+					pos = end;
+				}
+				signal([&] { piece_ready[i] = 1; });
+				return 0;
+			});
 		tasks.emplace_back([&] {
 			_scoped_event scope("write_blocks", event);
 			std::ostringstream out;
@@ -1134,29 +1205,6 @@ namespace qboot
 			write_file(root / "blocks.0", out.str(), nullptr, 0);
 			return 0;
 		});
-		// bilinear_bases.0: one piece of text per constraint ("rows cols" headers + numbers), formatted by the host pool in
-		// parallel (the device formats each piece's numbers) and written out back to back afterwards
-		vector<std::string> bl_pieces(J);
-		for (uint32_t i = 0; i < J; ++i)
-			tasks.emplace_back([&, i] {
-				vector<uint32_t> recs;
-				for (const auto& m : slots_[i]->bilinear()) append_records(recs, m, W);
-				std::string text;
-				vector<size_t> ends;
-				b200::format_numbers(*eng, nd, recs.data(), recs.size() / W, text, &ends);
-				std::string& out = bl_pieces[i];
-				out.reserve(text.size() + 64);
-				size_t pos = 0, num = 0;
-				for (const auto& m : slots_[i]->bilinear())
-				{
-					out += std::to_string(m.row()) + " " + std::to_string(m.column()) + "\n";
-					num += size_t(m.row()) * m.column();
-					const size_t end = num ? ends[num - 1] : 0;
-					out.append(text, pos, end - pos);
-					pos = end;
-				}
-				return 0;
-			});
 		tasks.emplace_back([&] {
 			_scoped_event scope("write_objectives", event);
 			vector<uint32_t> recs(offset_._words(), offset_._words() + W);
@@ -1169,21 +1217,9 @@ namespace qboot
 			write_file(root / "objectives", out, nullptr, 0);
 			return 0;
 		});
-		_parallel_evaluate(tasks, parallel);
-		tasks.clear();
-		if (text_thread.joinable()) text_thread.join();
-		if (text_error) std::rethrow_exception(text_error);
-		tasks.emplace_back([&] {
-			_scoped_event scope("write_bilinear_bases", event);
-			std::ofstream f(root / "bilinear_bases.0", std::ios::binary);
-			const std::string head = std::to_string(J) + "\n";
-			f.write(head.data(), std::streamsize(head.size()));
-			for (const auto& piece : bl_pieces) f.write(piece.data(), std::streamsize(piece.size()));
-			if (!f) throw std::runtime_error("qboot_b200: cannot write " + (root / "bilinear_bases.0").string());
-			return 0;
-		});
 		for (uint32_t i = 0; i < J; ++i)
 			tasks.emplace_back([&, i] {
+				if (!wait_for([&] { return text_ready; })) return 0;
 				_scoped_event scope("write constraint " + std::to_string(i), event);
 				const auto& c = slots_[i].value();
 				const std::string hb = std::to_string(c.schur_size()) + " " + std::to_string(c.num_free()) + "\n", hc = std::to_string(c.schur_size()) + "\n";
@@ -1208,7 +1244,20 @@ namespace qboot
 				}
 				return 0;
 			});
-		_parallel_evaluate(tasks, parallel);
+		try
+		{
+			_scoped_event scope("write: host pool", event);
+			_parallel_evaluate(tasks, parallel);
+		}
+		catch (...)
+		{
+			signal([&] { failed = true; });
+			throw;  // the joiners wait for the two threads
+		}
+		if (text_thread.joinable()) text_thread.join();
+		if (writer_thread.joinable()) writer_thread.join();
+		if (text_error) std::rethrow_exception(text_error);
+		if (writer_error) std::rethrow_exception(writer_error);
 	}
 	void SDPBInput::write(const fs::path& root, uint32_t parallel, const unique_ptr<_event_base>& event) const& { write_all(root, parallel, event); }
 	void SDPBInput::write(const fs::path& root, uint32_t parallel, const unique_ptr<_event_base>& event) &&
