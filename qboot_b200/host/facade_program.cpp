@@ -450,6 +450,19 @@ namespace qboot
 						it.samples = std::make_shared<BilinearSamples>(prepare_bilinear_samples(*it.scale, W));
 						return 0;
 					});
+			// largest first (the cost grows with the number of poles, i.e. with the degree): the pool hands tasks out in order, and
+			// a long task started last would be the tail of the phase
+			{
+				vector<std::pair<uint32_t, size_t>> order;
+				size_t k = 0;
+				for (auto& it : plan.items)
+					if (it.op_index >= 0 && it.scale) order.emplace_back(it.scale->max_degree(), k++);
+				std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+				vector<std::function<int()>> sorted;
+				sorted.reserve(tasks.size());
+				for (const auto& o : order) sorted.push_back(move(tasks[o.second]));
+				tasks.swap(sorted);
+			}
 			try
 			{
 				// one hardware thread is left to the thread that drives the GPU
