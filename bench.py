@@ -503,7 +503,7 @@ def main():
                                "note": "chunks serialised on one stream with an event around every stage; the timed step overlaps them"},
         "roofline": {"bound": "imad", "achieved": step_frac * peak / 1e12, "peak": peak / 1e12, "unit": "Tlimb-MAC/s", "frac": step_frac,
                      "traffic": ncu_traffic(n), "traffic_note": "DRAM bytes per step per GPU from the ncu capture of every kernel (profiles/r2_traffic.json); "
-                                                                "the path is multiply-bound, not HBM-bound: ~7.4 MB per table against 2.3e7 limb-MACs",
+                                                                "the path is multiply-bound, not HBM-bound: ~7.2 MB per table against 2.3e7 limb-MACs",
                      "kernel": "whole step (k_rec_coeffs, k_series, k_pow, k_scale, k_horner, k_rho_to_z, k_offdiag_*)",
                      "stages": stages,
                      "peak_source": "measured on this GPU by qb_imad_peak: dependency-free IMAD.WIDE.U32 chains at full occupancy "
