@@ -4,6 +4,7 @@
 //                   k_ops         diagnostic: one primitive elementwise
 //   kernels_g1.cuh  k_coef_fx     one thread per (polynomial, job): fixed-point frames of the recurrence polynomials -> coefx
 //                   k_series      one thread per series job over a front group: recurrence polynomials + the chain   -> b[job][0..n_max]
+//   kernels_g7.cuh  k_series_coop the same recurrence for small batches: eight warps (roles) per 32 jobs                   -> b
 //   kernels_g2.cuh  k_scale       one thread per (table, n): the lambda+1 scaled coefficient arrays -> a[table][k][n]
 //                   k_horner      one thread per (table, k): Horner sum, times rho^q / k!           -> fr[table][k]
 //   kernels_g3.cuh  k_rho_to_z, k_offdiag_val, k_offdiag_close: rho->z matrix and the transverse recursion, level by level -> g[table][dim_M]
